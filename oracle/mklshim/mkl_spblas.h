@@ -1,0 +1,2 @@
+/* MKL-compat shim (test infrastructure): see mkl.h */
+#include "mkl.h"
