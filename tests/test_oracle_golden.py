@@ -1,0 +1,169 @@
+"""CPU tests: the C restatement (oracle/sparsh_oracle.c) against the golden vectors produced by the reference itself
+(tests/golden/make_golden.py), and — when the prebuilt oracle/_ref library is present — against the reference live."""
+import hashlib
+
+import numpy as np
+import pytest
+from conftest import system_by_name
+from oracle_bindings import CSR, OracleAmg, Ref, RefAmg, have_ref
+
+CASES = ["fixture", "poisson3d_24_ones", "poisson3d_24_axstar", "poisson2d_96_ones", "poisson2d_96_axstar"]
+RTOL_HIST = 1e-10  # north_star: V-cycle / PCG residual histories within 1e-10 relative
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def assert_hist(got, want, rtol=RTOL_HIST):
+    got, want = np.asarray(got), np.asarray(want)
+    assert abs(len(got) - len(want)) <= 1, (len(got), len(want))  # north_star: same iteration count (+-1)
+    m = min(len(got), len(want))
+    np.testing.assert_allclose(got[:m], want[:m], rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize("case", CASES + ["poisson3d_40_ones"])
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_hierarchy_matches_reference(case, coarsening, oracle, fixture_system, golden):
+    A, b = system_by_name(case, oracle, fixture_system)
+    amg = OracleAmg(A, coarsening=0 if coarsening == "hem" else 1)
+    H = amg.hierarchy()
+    want = golden[case][coarsening]["levels"]
+    assert H.nlevels == len(want)
+    for L, w in zip(H.levels, want):
+        assert (L["A"].nrow, L["A"].nnz) == (w["nrow"], w["nnz"])
+        # integer data bit-exact
+        assert sha(L["A"].rowptr) == w["rowptr_sha"]
+        assert sha(L["A"].colindex) == w["colindex_sha"]
+        np.testing.assert_allclose(np.sum(L["A"].val), w["val_sum"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(np.sum(np.abs(L["A"].val)), w["val_abs_sum"], rtol=1e-12)
+        np.testing.assert_allclose(np.sum(L["diag"]), w["diag_sum"], rtol=1e-12)
+        if L["P"] is not None:
+            assert (L["P"].ncol, L["P"].nnz) == (w["p_ncol"], w["p_nnz"])
+            assert sha(L["P"].rowptr) == w["p_rowptr_sha"]
+            assert sha(L["P"].colindex) == w["p_colindex_sha"]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_amg_solve_history(case, coarsening, oracle, fixture_system, golden):
+    A, b = system_by_name(case, oracle, fixture_system)
+    amg = OracleAmg(A, coarsening=0 if coarsening == "hem" else 1)
+    x, hist = amg.solve(b, np.zeros(A.nrow), 1e-8)
+    assert_hist(hist[1:], golden[case][coarsening]["amg_solve_hist"])
+    np.testing.assert_allclose(np.sum(x), golden[case][coarsening]["amg_solve_x_sum"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_vcycle_probe_and_pcg(case, coarsening, oracle, fixture_system, golden):
+    A, b = system_by_name(case, oracle, fixture_system)
+    g = golden[case][coarsening]
+    amg = OracleAmg(A, coarsening=0 if coarsening == "hem" else 1)
+    xr = np.random.default_rng(g["vcycle_probe"]["seed"]).random(A.nrow)
+    x1 = amg.vcycle(b, xr, 1)
+    np.testing.assert_allclose(x1[:8], g["vcycle_probe"]["x_head"], rtol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(x1), g["vcycle_probe"]["x_norm"], rtol=1e-12)
+    x, hist = amg.pcg(b, np.zeros(A.nrow), 1e-8)
+    assert_hist(hist, g["pcg_hist"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_shipped_entry_points(case, oracle, fixture_system, golden):
+    """AMG_Solver_CPU_baseline / Solver_PCG_1 / Solver_PBiCG_1 exactly as shipped (HEM)."""
+    A, b = system_by_name(case, oracle, fixture_system)
+    g = golden[case]
+    amg = OracleAmg(A)
+    x0 = np.zeros(A.nrow)
+    _, h = amg.solve(b, x0, 1e-8)
+    assert_hist(h[1:], g["AMG_Solver_CPU_baseline"]["hist"])
+    _, h = amg.pcg(b, x0, 1e-8)
+    assert_hist(h[1:], g["Solver_PCG_1"]["hist"])
+    _, h = amg.pbicgstab(b, x0, 1e-8)
+    assert_hist(h[1:], g["Solver_PBiCG_1"]["hist"])
+
+
+def test_fixture_headline_counts(golden):
+    """SURVEY Appendix C / BASELINE.md §5: 30 cycles, 13 PCG its, 7 PBiCGStab its (HEM); 18 / 10 (Beck)."""
+    f = golden["fixture"]
+    assert len(f["AMG_Solver_CPU_baseline"]["hist"]) == 30
+    assert len(f["Solver_PCG_1"]["hist"]) == 13
+    assert len(f["Solver_PBiCG_1"]["hist"]) == 7
+    assert len(f["beck"]["amg_solve_hist"]) == 18
+    assert len(f["beck"]["pcg_hist"]) - 1 == 10
+    assert abs(f["AMG_Solver_CPU_baseline"]["hist"][0] - 0.35307) < 1e-5
+
+
+def test_unpreconditioned_krylov(oracle, fixture_system, golden):
+    A, b = fixture_system
+    n = A.nrow
+    from oracle_bindings import dp, ip
+
+    for fn, key in [(oracle.lib.so_cg, "Solver_CG_1"), (oracle.lib.so_bicgstab, "Solver_BiCG_1")]:
+        x = np.zeros(n)
+        hist = np.zeros(2001)
+        k = fn(n, ip(A.rowptr), ip(A.colindex), dp(A.val), dp(b), dp(x), 1e-8, 2000, dp(hist))
+        g = golden["fixture"][key]
+        # long unpreconditioned recurrences amplify rounding: count within 1%, first residuals tight
+        assert abs(k - g["iters"]) <= max(1, g["iters"] // 100)
+        np.testing.assert_allclose(hist[1:6], g["head"], rtol=1e-9)
+
+
+def test_coloring_and_sor(oracle, fixture_system, golden):
+    A, b = fixture_system
+    g = golden["fixture"]["coloring"]
+    nc, perm, cc, Q = oracle.color_reorder(A)
+    assert nc == g["total_colors"]
+    assert cc.tolist() == g["color_count"]
+    assert sha(perm) == g["perm_sha"]  # integer permutation bit-exact
+    assert sha(Q.rowptr) == g["q_rowptr_sha"] and sha(Q.colindex) == g["q_colindex_sha"]
+    xs = oracle.sor_multicolor(Q, Q.diagonal(), cc, b[perm], np.zeros(A.nrow), 0.66667, 3)
+    np.testing.assert_allclose(xs[:8], golden["fixture"]["sor_probe"]["x_head"], rtol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(xs), golden["fixture"]["sor_probe"]["x_norm"], rtol=1e-12)
+
+
+def test_direct_solver_accuracy(oracle):
+    A = oracle.gen_poisson3d(14, 14, 14)
+    xs = np.random.default_rng(3).random(A.nrow)
+    b = A.to_scipy() @ xs
+    x = oracle.lu_solve(A, b)
+    np.testing.assert_allclose(x, xs, rtol=1e-11)
+
+
+def test_edge_cases(oracle):
+    # 1x1, diagonal-only, and a ragged matrix with an empty row
+    A = CSR(1, 1, [0, 1], [0], [2.0])
+    assert oracle.spmv(A, np.array([3.0]))[0] == 6.0
+    A = CSR(3, 3, [0, 2, 2, 3], [0, 2, 2], [1.0, 2.0, 4.0])
+    np.testing.assert_array_equal(oracle.spmv(A, np.array([1.0, 5.0, 2.0])), [5.0, 0.0, 8.0])
+    P = CSR(3, 2, [0, 1, 2, 3], [0, 0, 1], [1.0, 1.0, 1.0])
+    np.testing.assert_array_equal(oracle.transfer_residual(P, np.array([1.0, 2.0, 4.0])), [3.0, 4.0])
+    np.testing.assert_array_equal(oracle.transfer_solution(P, np.array([10.0, 20.0]), np.array([1.0, 1.0, 1.0])),
+                                  [11.0, 11.0, 21.0])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("coarsening", [0, 1])
+def test_primitives_against_live_reference(coarsening, oracle, fixture_system):
+    """Per-op parity (1e-12) between the restatement and the reference compiled here, every level."""
+    A, b = fixture_system
+    Ref.get().set_threads(4)
+    ref = RefAmg(A, coarsening)
+    H = ref.hierarchy()
+    rng = np.random.default_rng(11)
+    for k, L in enumerate(H.levels):
+        M, d = L["A"], L["diag"]
+        x, bb = rng.random(M.nrow), rng.random(M.nrow)
+        np.testing.assert_allclose(oracle.spmv(M, x), ref.spmv(k, x), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(oracle.jacobi(M, d, bb, x, 0.66667, 6), ref.jacobi(k, bb, x, 6), rtol=1e-12)
+        np.testing.assert_allclose(oracle.store_residual(M, bb, x), ref.store_residual(k, bb, x), rtol=1e-12,
+                                   atol=1e-14)
+        np.testing.assert_allclose(oracle.residual(M, bb, x), ref.residual(k, bb, x), rtol=1e-12)
+        if L["P"] is not None:
+            xc = rng.random(L["P"].ncol)
+            np.testing.assert_allclose(oracle.transfer_residual(L["P"], x), ref.transfer_residual(k, x), rtol=1e-12)
+            np.testing.assert_allclose(oracle.transfer_solution(L["P"], xc, x), ref.transfer_solution(k, xc, x),
+                                       rtol=1e-12)
+    last = H.levels[-1]["A"]
+    bb = rng.random(last.nrow)
+    np.testing.assert_allclose(oracle.lu_solve(last, bb), ref.coarse_solve(bb), rtol=1e-10)
