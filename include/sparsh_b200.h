@@ -1,0 +1,183 @@
+/*
+ * sparsh_b200.h — C-ABI of the B200-native AMG solve phase (libsparsh_b200.so).
+ *
+ * This is the drop-in boundary.  The reference (cmgcds/SParSH-AMG) has no FFI layer: its host C++
+ * (src/AMG_main_solvers.cpp, src/AMG_main_solvers.cu, src/AMG_gpu_phases*.cu) reaches the GPU through the
+ * class sp_matrix_gpu and through direct cuSPARSE/cuBLAS/thrust calls.  Every entry point below names the
+ * reference interface (file:line, relative to /root/reference) it replaces.  INTEGRATION.md shows the
+ * reference-side code that binds to it.
+ *
+ * Conventions
+ *  - plain C, no C++/torch/AMG.hpp types; `int` status return (0 = SPARSH_OK), message via sparsh_last_error()
+ *  - matrices are the reference's 0-based int32/fp64 CSR (include/AMG_matrix.hpp:6-32)
+ *  - `const double *d_*` / `double *d_*` arguments are DEVICE pointers, `h_*` are HOST pointers
+ *  - everything is stream-ordered on the library's current stream (sparsh_set_stream / sparsh_get_stream);
+ *    calls that return a scalar to the host synchronise that stream
+ *  - fp64 throughout, no tensor cores, no cuSPARSE/cuBLAS, no CPU fallback: a missing GPU is an error
+ *  - one handle per host thread (the reference is not re-entrant either: SURVEY §8b)
+ */
+#ifndef SPARSH_B200_H_
+#define SPARSH_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPARSH_OK 0
+#define SPARSH_ERR_CUDA 1
+#define SPARSH_ERR_INVALID 2
+#define SPARSH_ERR_NOT_CONVERGED 3
+#define SPARSH_ERR_NO_DEVICE 4
+
+typedef struct sparsh_matrix_s *sparsh_matrix_t;       /* replaces class sp_matrix_gpu (include/AMG_gpu_matrix.hpp:10-48) */
+typedef struct sparsh_hierarchy_s *sparsh_hierarchy_t; /* replaces the device state of AMG_GPU1_solver / AMG_GPU_solver
+                                                          (include/AMG_gpu_phases_2.hpp:9-40, AMG_gpu_phases.hpp:10-55) */
+
+/* ------------------------------------------------------------------ runtime ---- */
+int sparsh_init(int device);               /* cudaSetDevice + library stream; idempotent */
+int sparsh_shutdown(void);
+const char *sparsh_last_error(void);
+int sparsh_set_stream(void *cuda_stream);  /* adopt a caller stream (cudaStream_t); NULL restores the library's own */
+int sparsh_get_stream(void **cuda_stream);
+int sparsh_sync(void);                     /* replaces the cudaStreamSynchronize/cudaDeviceSynchronize pairs, e.g.
+                                              src/AMG_gpu_phases_2.cu:106-108 */
+int sparsh_device_name(char *buf, size_t len, int *sm_count);
+/* number of kernels this library has launched since the last reset (graph replays count their kernel nodes) */
+long long sparsh_launch_count(void);
+void sparsh_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ memory ----- */
+/* replace cudaMalloc / cudaMemcpy / thrust::fill of src/AMG_gpu_phases_2.cu:17-29,127,245-246,259 */
+int sparsh_malloc(size_t bytes, void **d_ptr);
+int sparsh_free(void *d_ptr);
+int sparsh_host_alloc(size_t bytes, void **h_ptr); /* pinned; replaces cudaHostRegister pinning,
+                                                      src/AMG_gpu_phase_utilities.cu:11-67 */
+int sparsh_host_free(void *h_ptr);
+int sparsh_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
+int sparsh_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
+int sparsh_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes);
+int sparsh_fill(double *d_x, size_t n, double value);
+
+/* ------------------------------------------------------------------ matrix ----- */
+/* sp_matrix_gpu::sp_matrix_gpu + matrix_transfer_gpu (src/AMG_gpu_matrix.cu:26-102): upload a host CSR.
+ * h_diag may be NULL: the diagonal is then extracted like sp_matrix_fill_diagonal (src/AMG_cpu_matrix.cpp:35-51). */
+int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex,
+                         const double *h_val, const double *h_diag, sparsh_matrix_t *out);
+/* explicit R = P^T (stable: each R row lists fine rows ascending), built once; replaces the transposed csrmv of
+ * src/AMG_gpu_phases_2.cu:125,186 / src/AMG_gpu_phases.cu:512 with a deterministic gather */
+int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex,
+                                   const double *h_val, sparsh_matrix_t *out);
+int sparsh_matrix_destroy(sparsh_matrix_t A); /* sp_matrix_gpu::~sp_matrix_gpu (src/AMG_gpu_matrix.cu:131-142) */
+int sparsh_matrix_dims(sparsh_matrix_t A, int *nrow, int *ncol, int *nnz);
+/* kernel family chosen at upload: 0 scalar (<=2.5 nnz/row), 1 stream (TMA-staged, thread per row), 2 vector
+ * (sub-warp per row).  sparsh_matrix_force_kernel overrides it (tests exercise every family). */
+int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, int *smem_bytes);
+int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int threads_or_lanes);
+
+/* ------------------------------------------------------------------ per-op ----- */
+/* K9  y = A x                              cusparseDcsrmv, e.g. src/AMG_main_solvers.cu:100,221,354 */
+int sparsh_spmv(sparsh_matrix_t A, const double *d_x, double *d_y);
+/* K9+K8  y = A x and *d_dot = x . y fused   csrmv + cublasDdot, src/AMG_main_solvers.cu:354-357 */
+int sparsh_spmv_dot(sparsh_matrix_t A, const double *d_x, double *d_y, double *d_dot);
+/* K2  r = b - A x                          csrmv(-1)+daxpy, src/AMG_gpu_phases_2.cu:181-183;
+ *                                          parallel::store_residual, src/AMG_cycle_utilities.cpp:115-123 */
+int sparsh_residual(sparsh_matrix_t A, const double *d_b, const double *d_x, double *d_r);
+/* K3  *h_norm = ||A x - b||_2 (nothing stored)   residual(), src/AMG_gpu_phase_utilities.cu:138-167;
+ *                                          parallel::residual, src/AMG_cycle_utilities.cpp:83-94 */
+int sparsh_residual_norm(sparsh_matrix_t A, const double *d_b, const double *d_x, double *h_norm);
+/* K1  `sweeps` fused weighted-Jacobi sweeps x <- x + (omega*(b - A x))/d, result left in d_x; d_tmp is an
+ * nrow scratch vector.                     sp_matrix_gpu::smooth_jacobi + jacobi_update, src/AMG_gpu_matrix.cu:15-22,
+ *                                          106-127; parallel::jacobi_smoother, src/AMG_smoothers.cpp:53-76
+ * (the CPU reference runs smooth_iter+1 = 7 sweeps, the GPU reference 6: SURVEY F7 — the count is an argument) */
+int sparsh_jacobi(sparsh_matrix_t A, const double *d_b, double *d_x, double *d_tmp, double omega, int sweeps);
+/* K6  multicolour SOR on a colour-permuted matrix: for each colour k, rows h_color_count[k]..[k+1] updated in
+ * place, x_l -= (omega*(sum_j a_lj x_j - b_l))/d_l.   parallel::sor_smoother, src/AMG_smoothers.cpp:78-102 (no GPU
+ * version exists in the reference: "SOR ... to be defined", src/AMG_gpu_matrix.cu:129) */
+int sparsh_mc_sor(sparsh_matrix_t A, const int *h_color_count, int total_colors, const double *d_b, double *d_x,
+                  double omega, int sweeps);
+/* K4  bc = R r with R = P^T explicit       transposed csrmv, src/AMG_gpu_phases_2.cu:186;
+ *                                          parallel::transfer_residual, src/AMG_cycle_utilities.cpp:97-104 */
+int sparsh_restrict(sparsh_matrix_t R, const double *d_r, double *d_bc);
+/* K5  xf += P xc                            csrmv beta=1, src/AMG_gpu_phases_2.cu:210;
+ *                                          parallel::transfer_solution, src/AMG_cycle_utilities.cpp:107-112 */
+int sparsh_prolong_add(sparsh_matrix_t P, const double *d_xc, double *d_xf);
+
+/* K8  BLAS-1 (replace cublasDdot/Dnrm2/Daxpy and the kernels daxpby/daxpbyc, src/AMG_main_solvers.cu:17-33).
+ * Reductions are two-stage with a fixed tree: bit-reproducible run to run. */
+int sparsh_dot(size_t n, const double *d_x, const double *d_y, double *h_out);
+int sparsh_nrm2(size_t n, const double *d_x, double *h_out);
+int sparsh_axpy(size_t n, double a, const double *d_x, double *d_y);                 /* y += a x          */
+int sparsh_axpby(size_t n, double a, const double *d_x, double b, double *d_y);      /* y = a x + b y     */
+int sparsh_axpbypcz(size_t n, double a, const double *d_x, double b, const double *d_y, double c,
+                    double *d_z);                                                   /* z = a x + b y + c z */
+
+/* ------------------------------------------------------------------ hierarchy -- */
+typedef struct {
+    /* A_l (square) */
+    int nrow, nnz;
+    const int *rowptr, *colindex;
+    const double *val, *diag; /* diag may be NULL */
+    /* P_l : nrow x p_ncol, NULL/0 on the coarsest level */
+    int p_ncol, p_nnz;
+    const int *p_rowptr, *p_colindex;
+    const double *p_val;
+} sparsh_level_desc;
+
+typedef struct {
+    double omega;     /* include/AMG.hpp:16   (0.66667)                                          */
+    int pre_sweeps;   /* Jacobi sweeps before restriction: 7 = CPU reference, 6 = GPU reference  */
+    int post_sweeps;  /* Jacobi sweeps after prolongation                                        */
+    int use_graph;    /* capture V-cycle / Krylov iterations into CUDA graphs (1) or launch directly (0) */
+    int coarse_mode;  /* 0: dense inverse formed on the device at setup, applied as a GEMV (K7)  */
+} sparsh_params;
+void sparsh_params_default(sparsh_params *p);
+
+/* AMG_GPU1_solver::GPU_Allocations (src/AMG_gpu_phases_2.cu:13-94): upload every A_l, P_l once, build R_l = P_l^T,
+ * factor the coarsest level (Direct_Solver_Pardiso ctor, src/AMG_coarse_level_solver.cpp:9-62, done on the device). */
+int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const sparsh_params *params,
+                            sparsh_hierarchy_t *out);
+int sparsh_hierarchy_destroy(sparsh_hierarchy_t h); /* AMG_GPU1_solver::~AMG_GPU1_solver, src/AMG_gpu_phases_2.cu:265-338 */
+int sparsh_hierarchy_nlevels(sparsh_hierarchy_t h);
+/* borrow the device matrices of one level (for per-op parity tests); P and R are NULL on the coarsest level */
+int sparsh_hierarchy_level(sparsh_hierarchy_t h, int level, sparsh_matrix_t *A, sparsh_matrix_t *P,
+                           sparsh_matrix_t *R);
+/* K7  x = A_L^{-1} b on the coarsest level   Direct_Solver_Pardiso_solve, src/AMG_coarse_level_solver.cpp:64-76 (host
+ * PARDISO + 2 PCIe hops per cycle in the reference, src/AMG_gpu_phases_2.cu:192-203) */
+int sparsh_hierarchy_coarse_solve(sparsh_hierarchy_t h, const double *d_b, double *d_x);
+/* V  exactly `cycles` V(pre,post)-cycles on device b, x (x in/out).  AMG_GPU1_solver::AMG_Solve(b,x,iterations>0),
+ * src/AMG_gpu_phases_2.cu:109-170; AMG_solver::AMG_solve_jacobi(b,x,k), src/AMG_phases.cpp:163-192.
+ * x_is_zero != 0 promises x == 0 on entry (preconditioner use): the first pre-sweep then needs no matrix pass. */
+int sparsh_hierarchy_vcycle(sparsh_hierarchy_t h, const double *d_b, double *d_x, int cycles, int x_is_zero);
+/* AMG as a solver: V-cycles until ||A x - b||_2 <= tol (absolute, as the reference) or max_cycles.
+ * AMG_Solve(b,x,-1), src/AMG_gpu_phases_2.cu:171-236; AMG_solve_jacobi(b,x,-1), src/AMG_phases.cpp:194-226.
+ * h_hist (may be NULL) receives hist[0] = initial residual, hist[k] = residual after cycle k (max_cycles+1 slots). */
+int sparsh_hierarchy_amg_solve(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int max_cycles,
+                               double *h_hist, int *cycles);
+/* S1  AMG-preconditioned CG on the device.  Solver_PCG_4 / Solver_PCG_3 (src/AMG_main_solvers.cu:142-413) with the
+ * arithmetic of Solver_PCG_1 (src/AMG_main_solvers.cpp:107-167).  hist[0] = ||b - A x0||, hist[k] after iteration k. */
+int sparsh_hierarchy_pcg(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int max_iter,
+                         double *h_hist, int *iters);
+/* S2  AMG-preconditioned BiCGStab.  Solver_PBiCG_3/4 (src/AMG_main_solvers.cu:416-763) with the arithmetic of
+ * Solver_PBiCG_1 (src/AMG_main_solvers.cpp:358-458; the GPU twins are defective). */
+int sparsh_hierarchy_pbicgstab(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int max_iter,
+                               double *h_hist, int *iters);
+/* Unpreconditioned twins: Solver_CG_2 (src/AMG_main_solvers.cu:35-139; arithmetic of Solver_CG_1,
+ * src/AMG_main_solvers.cpp:47-103, which assumes x0 = 0) and Solver_BiCG_1 (src/AMG_main_solvers.cpp:271-355). */
+int sparsh_cg(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int max_iter, double *h_hist,
+              int *iters);
+int sparsh_bicgstab(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int max_iter, double *h_hist,
+                    int *iters);
+/* Host-buffer wrappers (the reference's AMG_GPU1_solver::helper, src/AMG_gpu_phases_2.cu:242-263, and the
+ * cudaMemcpy prologue/epilogue of Solver_PCG_4, src/AMG_main_solvers.cu:311-312,392): H2D of b and x, solve,
+ * D2H of x.  method: 0 = AMG as solver, 1 = PCG, 2 = PBiCGStab. */
+int sparsh_hierarchy_solve_host(sparsh_hierarchy_t h, int method, const double *h_b, double *h_x, double tol,
+                                int max_iter, double *h_hist, int *iters);
+/* bytes moved by one V-cycle according to the algorithmic model of SURVEY §8d (for roofline reports) */
+double sparsh_hierarchy_vcycle_bytes(sparsh_hierarchy_t h, int x_is_zero);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSH_B200_H_ */

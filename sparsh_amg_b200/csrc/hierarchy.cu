@@ -1,0 +1,234 @@
+// hierarchy.cu — hierarchy upload and the V-cycle (row V of SURVEY §8a).
+//
+// Replaces AMG_GPU1_solver::GPU_Allocations / AMG_Solve (reference src/AMG_gpu_phases_2.cu:13-240) and
+// AMG_GPU_solver (src/AMG_gpu_phases.cu:13-459).  Cycle semantics follow AMG_solver::AMG_solve_jacobi
+// (src/AMG_phases.cpp:151-230), the only runnable oracle:
+//   down: Jacobi(A_l,B_l,X_l) -> R_l = B_l - A_l X_l -> B_{l+1} = P_l^T R_l -> X_{l+1} = 0
+//   bottom: X_L = A_L^{-1} B_L
+//   up:   X_{l-1} += P_{l-1} X_l -> Jacobi(A_{l-1},B_{l-1},X_{l-1})
+// One fused kernel per Jacobi sweep (out of place, ping-pong), one per residual, restriction and
+// prolongation-correction; the first sweep after "X = 0" needs no matrix pass at all (A*0 = 0 exactly).
+// The whole cycle is captured into a CUDA graph: a 14-level hierarchy is ~250 launches, most of them on levels too
+// small to hide launch latency otherwise.
+#include <cmath>
+#include <utility>
+
+#include "hierarchy.cuh"
+
+using namespace sparsh;
+
+namespace sparsh {
+
+static int smooth(sparsh_hierarchy_s *h, Level &L, const double *b, double *&cur, double *&other, int sweeps,
+                  bool zero_guess) {
+    if (sweeps == 0) {
+        if (zero_guess) SP_TRY(k_fill(cur, (size_t)L.n, 0.0));
+        return SPARSH_OK;
+    }
+    for (int s = 0; s < sweeps; s++) {
+        if (s == 0 && zero_guess) {
+            SP_TRY(k_jacobi_zero((size_t)L.n, b, L.A->diag, h->prm.omega, other));
+        } else {
+            EpiArgs a;
+            a.b = b;
+            a.xi = cur;
+            a.d = L.A->diag;
+            a.omega = h->prm.omega;
+            SP_TRY(launch_csr(L.A, EPI_JACOBI, cur, other, a, 0, L.n));
+        }
+        std::swap(cur, other);
+    }
+    return SPARSH_OK;
+}
+
+int enqueue_vcycle(sparsh_hierarchy_s *h, const double *b, double *x, bool x_is_zero) {
+    Context &c = ctx();
+    const int L = (int)h->lev.size() - 1;
+    // canonical buffers at the start of every cycle (so a captured graph replays identically)
+    std::vector<double *> X(L + 1), T(L + 1);
+    std::vector<const double *> B(L + 1);
+    for (int l = 0; l <= L; l++) {
+        X[l] = l == 0 ? x : h->lev[l].xbuf;
+        T[l] = h->lev[l].tbuf;
+        B[l] = l == 0 ? b : h->lev[l].bbuf;
+    }
+    for (int l = 0; l < L; l++) {
+        Level &F = h->lev[l];
+        SP_TRY(smooth(h, F, B[l], X[l], T[l], h->prm.pre_sweeps, l > 0 || x_is_zero));
+        EpiArgs a;
+        a.b = B[l];
+        SP_TRY(launch_csr(F.A, EPI_RESID, X[l], F.rbuf, a, 0, F.n));
+        SP_TRY(launch_csr(F.R, EPI_SPMV, F.rbuf, h->lev[l + 1].bbuf, EpiArgs(), 0, F.R->nrow));
+    }
+    if (L == 0 && h->coarse.n == 0) {
+        set_error("hierarchy without a coarse solver");
+        return SPARSH_ERR_INVALID;
+    }
+    SP_TRY(coarse_apply(h->coarse, B[L], X[L]));
+    for (int l = L; l > 0; l--) {
+        Level &F = h->lev[l - 1];
+        SP_TRY(launch_csr(F.P, EPI_PROLONG, X[l], X[l - 1], EpiArgs(), 0, F.n));
+        SP_TRY(smooth(h, F, B[l - 1], X[l - 1], T[l - 1], h->prm.post_sweeps, false));
+    }
+    if (X[0] != x) SP_CUDA(cudaMemcpyAsync(x, X[0], sizeof(double) * (size_t)h->lev[0].n, cudaMemcpyDeviceToDevice, c.stream));
+    return SPARSH_OK;
+}
+
+int krylov_workspace(sparsh_hierarchy_s *h, int nvec) {
+    const size_t n = (size_t)h->lev[0].n;
+    for (int i = 0; i < nvec; i++)
+        if (!h->kv[i]) SP_CUDA(cudaMalloc(&h->kv[i], sizeof(double) * (n + 2)));
+    return SPARSH_OK;
+}
+
+}  // namespace sparsh
+
+extern "C" {
+
+void sparsh_params_default(sparsh_params *p) {
+    p->omega = 0.66667;  // reference include/AMG.hpp:16
+    p->pre_sweeps = 7;   // smooth_iter + 1: the CPU reference's count (src/AMG_smoothers.cpp:60)
+    p->post_sweeps = 7;
+    p->use_graph = 1;
+    p->coarse_mode = 0;
+}
+
+int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const sparsh_params *params,
+                            sparsh_hierarchy_t *out) {
+    SP_TRY(ensure_init());
+    SP_REQUIRE(nlevels >= 1 && levels != nullptr && out != nullptr, "bad hierarchy description");
+    sparsh_hierarchy_s *h = new sparsh_hierarchy_s();
+    if (params)
+        h->prm = *params;
+    else
+        sparsh_params_default(&h->prm);
+    h->lev.resize(nlevels);
+    int rc = SPARSH_OK;
+    for (int l = 0; l < nlevels && rc == SPARSH_OK; l++) {
+        const sparsh_level_desc &d = levels[l];
+        Level &L = h->lev[l];
+        L.n = d.nrow;
+        rc = sparsh_matrix_create(d.nrow, d.nrow, d.nnz, d.rowptr, d.colindex, d.val, d.diag, &L.A);
+        if (rc != SPARSH_OK) break;
+        const size_t bytes = sizeof(double) * ((size_t)d.nrow + 2);
+        if (cudaMalloc(&L.tbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+        if (l > 0 && rc == SPARSH_OK) {
+            if (cudaMalloc(&L.xbuf, bytes) != cudaSuccess || cudaMalloc(&L.bbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+        }
+        if (l < nlevels - 1 && rc == SPARSH_OK) {
+            if (d.p_rowptr == nullptr || d.p_ncol != levels[l + 1].nrow) {
+                set_error("prolongator missing or its column count differs from the next level's row count");
+                rc = SPARSH_ERR_INVALID;
+                break;
+            }
+            if (cudaMalloc(&L.rbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+            if (rc == SPARSH_OK)
+                rc = sparsh_matrix_create(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, nullptr, &L.P);
+            if (rc == SPARSH_OK)
+                rc = sparsh_matrix_create_transpose(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, &L.R);
+        }
+    }
+    if (rc == SPARSH_OK) {
+        const sparsh_level_desc &d = levels[nlevels - 1];
+        rc = coarse_build_inverse(d.nrow, d.rowptr, d.colindex, d.val, &h->coarse);
+    }
+    if (rc == SPARSH_OK && cudaMalloc(&h->d_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+    if (rc == SPARSH_OK && cudaMallocHost(&h->h_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+    if (rc != SPARSH_OK) {
+        if (rc == SPARSH_ERR_CUDA) set_error(std::string("hierarchy allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        sparsh_hierarchy_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SPARSH_OK;
+}
+
+int sparsh_hierarchy_destroy(sparsh_hierarchy_t h) {
+    if (!h) return SPARSH_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    for (auto &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto &L : h->lev) {
+        sparsh_matrix_destroy(L.A);
+        sparsh_matrix_destroy(L.P);
+        sparsh_matrix_destroy(L.R);
+        cudaFree(L.xbuf);
+        cudaFree(L.tbuf);
+        cudaFree(L.bbuf);
+        cudaFree(L.rbuf);
+    }
+    coarse_free(&h->coarse);
+    for (int i = 0; i < 8; i++) cudaFree(h->kv[i]);
+    cudaFree(h->d_sc);
+    cudaFreeHost(h->h_sc);
+    cudaFree(h->hb);
+    cudaFree(h->hx);
+    delete h;
+    return SPARSH_OK;
+}
+
+int sparsh_hierarchy_nlevels(sparsh_hierarchy_t h) { return h ? (int)h->lev.size() : 0; }
+
+int sparsh_hierarchy_level(sparsh_hierarchy_t h, int level, sparsh_matrix_t *A, sparsh_matrix_t *P, sparsh_matrix_t *R) {
+    SP_REQUIRE(h != nullptr && level >= 0 && level < (int)h->lev.size(), "bad level");
+    if (A) *A = h->lev[level].A;
+    if (P) *P = h->lev[level].P;
+    if (R) *R = h->lev[level].R;
+    return SPARSH_OK;
+}
+
+int sparsh_hierarchy_coarse_solve(sparsh_hierarchy_t h, const double *d_b, double *d_x) {
+    SP_REQUIRE(h != nullptr, "hierarchy is NULL");
+    return coarse_apply(h->coarse, d_b, d_x);
+}
+
+int sparsh_hierarchy_vcycle(sparsh_hierarchy_t h, const double *d_b, double *d_x, int cycles, int x_is_zero) {
+    SP_REQUIRE(h != nullptr && cycles >= 0, "bad arguments");
+    for (int k = 0; k < cycles; k++) {
+        const bool zero = x_is_zero && k == 0;
+        SP_TRY(run_graphed(h, d_b, d_x, zero ? 1 : 0, [&]() { return enqueue_vcycle(h, d_b, d_x, zero); }));
+    }
+    return SPARSH_OK;
+}
+
+int sparsh_hierarchy_amg_solve(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int max_cycles,
+                               double *h_hist, int *cycles_out) {
+    SP_REQUIRE(h != nullptr, "hierarchy is NULL");
+    sparsh_matrix_s *A = h->lev[0].A;
+    double r1 = 0.0;
+    SP_TRY(sparsh_residual_norm(A, d_b, d_x, &r1));  // reference src/AMG_phases.cpp:159
+    if (h_hist) h_hist[0] = r1;
+    int cycles = 0;
+    while (r1 > tol && cycles < max_cycles) {         // :196 (the reference has no cap: SURVEY F6)
+        SP_TRY(sparsh_hierarchy_vcycle(h, d_b, d_x, 1, 0));
+        cycles++;
+        SP_TRY(sparsh_residual_norm(A, d_b, d_x, &r1));  // :219
+        if (h_hist) h_hist[cycles] = r1;
+        if (!std::isfinite(r1)) break;
+    }
+    if (cycles_out) *cycles_out = cycles;
+    return (r1 <= tol) ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
+}
+
+double sparsh_hierarchy_vcycle_bytes(sparsh_hierarchy_t h, int x_is_zero) {
+    if (!h) return 0.0;
+    const int L = (int)h->lev.size() - 1;
+    double total = 0.0;
+    for (int l = 0; l < L; l++) {
+        const Level &F = h->lev[l];
+        const double m = F.n, z = F.A->nnz, zp = F.P->nnz, mc = h->lev[l + 1].n;
+        const double jac = 12.0 * z + 4.0 * (m + 1) + 32.0 * m;
+        const double res = 12.0 * z + 4.0 * (m + 1) + 8.0 * m + 16.0 * m;
+        const double rst = 12.0 * zp + 4.0 * (mc + 1) + 8.0 * m + 8.0 * mc;
+        const double pro = 12.0 * zp + 4.0 * (m + 1) + 16.0 * m + 8.0 * mc;
+        const bool zero = l > 0 || x_is_zero;
+        double pre = h->prm.pre_sweeps * jac;
+        if (zero && h->prm.pre_sweeps > 0) pre += -jac + 24.0 * m;  // first sweep is x = (omega*b)/d
+        total += pre + res + rst + pro + h->prm.post_sweeps * jac;
+    }
+    const double nl = h->coarse.n;
+    total += 8.0 * nl * nl + 16.0 * nl;
+    return total;
+}
+
+}  // extern "C"

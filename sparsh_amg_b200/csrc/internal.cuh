@@ -1,0 +1,145 @@
+// internal.cuh — shared declarations of libsparsh_b200 (never includes the reference's AMG.hpp: its macros
+// `th`, `omega`, ... break CUDA headers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sparsh_b200.h"
+
+namespace sparsh {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SP_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::sparsh::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define SP_TRY(call)                      \
+    do {                                  \
+        int rc__ = (call);                \
+        if (rc__ != SPARSH_OK) return rc__; \
+    } while (0)
+#define SP_REQUIRE(cond, msg)             \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::sparsh::set_error(msg);     \
+            return SPARSH_ERR_INVALID;    \
+        }                                 \
+    } while (0)
+
+// ---- runtime context --------------------------------------------------------------------------------
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;  // kernels launched (direct) + kernel nodes replayed (graphs)
+    bool capturing = false;  // launches issued while capturing are counted per replay instead
+    long long captured = 0;
+    // reduction workspace (two-stage deterministic reductions)
+    double *partials = nullptr;  // RED_MAX_BLOCKS * RED_MAX_VALUES doubles
+    unsigned int *ticket = nullptr;
+    double *d_scalar = nullptr;  // small device scratch for scalar results (16 doubles)
+    double *h_scalar = nullptr;  // pinned mirror
+};
+Context &ctx();
+int ensure_init();
+inline void count_launch() {
+    Context &c = ctx();
+    if (c.capturing)
+        c.captured++;
+    else
+        c.launches++;
+}
+
+constexpr int RED_MAX_BLOCKS = 1 << 18;  // enough for 2^26 rows at 256 rows per block
+constexpr int RED_MAX_VALUES = 4;
+
+// ---- device CSR ---------------------------------------------------------------------------------------
+enum KernelKind { KIND_SCALAR = 0, KIND_STREAM = 1, KIND_VECTOR = 2 };
+
+struct CsrView {
+    int nrow, ncol, nnz;
+    const int *__restrict__ rowptr;
+    const int *__restrict__ col;
+    const double *__restrict__ val;
+};
+
+}  // namespace sparsh
+
+struct sparsh_matrix_s {
+    int nrow = 0, ncol = 0, nnz = 0;
+    int *rowptr = nullptr;  // nrow+1 (+ padding)
+    int *col = nullptr;     // nnz padded to a multiple of 4, +8
+    double *val = nullptr;
+    double *diag = nullptr;  // nrow, or null for rectangular operators
+    // kernel selection (made at upload from host-side row statistics)
+    int kind = sparsh::KIND_VECTOR;
+    int threads = 256;  // stream/scalar: rows per CTA == threads per CTA
+    int lanes = 8;      // vector: lanes per row
+    int max_row = 0;
+    double mean_row = 0.0;
+    int win128 = 0, win256 = 0;  // max nnz over any window of 128 / 256 consecutive rows
+    int smem_bytes = 0;          // dynamic shared memory of the stream kernel
+    sparsh::CsrView view() const { return sparsh::CsrView{nrow, ncol, nnz, rowptr, col, val}; }
+};
+
+namespace sparsh {
+
+// ---- SpMV family (spmv.cu) ----------------------------------------------------------------------------
+// y_i = epilogue(sum_j a_ij x_j) over rows [row_begin,row_end)
+enum EpiKind {
+    EPI_SPMV = 0,      // y = s
+    EPI_RESID = 1,     // y = b - s
+    EPI_JACOBI = 2,    // y = xi + (omega*(b - s))/d
+    EPI_PROLONG = 3,   // y = s + y
+    EPI_SOR = 4,       // y = y - (omega*(s - b))/d              (in place, one colour)
+    EPI_SPMV_DOT = 5,  // y = s, reduce x_i*s
+    EPI_RESNORM = 6    // reduce (s - b)^2, nothing stored
+};
+struct EpiArgs {
+    const double *b = nullptr;
+    const double *xi = nullptr;  // the "own" x entry stream (same array as the gathered x for Jacobi)
+    const double *d = nullptr;
+    double omega = 0.0;
+    double *red_out = nullptr;  // device scalar receiving the reduction (EPI_SPMV_DOT / EPI_RESNORM)
+};
+int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
+               int row_end);
+
+// ---- BLAS-1 (blas1.cu) -------------------------------------------------------------------------------------
+int k_fill(double *x, size_t n, double v);
+int k_axpy(size_t n, double a, const double *x, double *y);
+int k_axpby(size_t n, double a, const double *x, double b, double *y);
+int k_axpbypcz(size_t n, double a, const double *x, double b, const double *y, double c, double *z);
+int k_dot(size_t n, const double *x, const double *y, double *d_out);        // d_out[0] = x.y
+int k_jacobi_zero(size_t n, const double *b, const double *d, double omega, double *x);  // x = (omega*b)/d
+// Krylov fused updates; scalars live in device memory (s[] indices documented in krylov.cu)
+int k_pcg_update_xr(size_t n, const double *p, const double *Ap, double *x, double *r, const double *rz,
+                    const double *pAp, double *rr_out);
+int k_pcg_update_p(size_t n, const double *z, double *p, const double *rz_new, const double *rz_old);
+int k_scalar_copy(double *dst, const double *src);
+int k_cg_update_p(size_t n, const double *r, double *p, const double *rr_new, const double *rr_old);
+int k_bicg_s(size_t n, const double *r, const double *Ap, double *s, const double *alpha1, const double *apr0);
+int k_bicg_xr(size_t n, double *x, const double *ph, const double *sh, const double *s, const double *As, double *r,
+              const double *alpha1, const double *apr0, const double *ass, const double *asas, const double *r0,
+              double *out2);
+int k_bicg_p(size_t n, const double *r, double *p, const double *Ap, const double *sc);
+int k_dot2(size_t n, const double *a, const double *b, const double *c, double *d_out2);  // out[0]=a.b out[1]=a.c
+
+// ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------
+struct CoarseInverse {
+    int n = 0;
+    double *inv = nullptr;  // n x n row-major
+};
+int coarse_build_inverse(int n, const int *h_rowptr, const int *h_col, const double *h_val, CoarseInverse *out);
+int coarse_apply(const CoarseInverse &ci, const double *b, double *x);
+void coarse_free(CoarseInverse *ci);
+
+}  // namespace sparsh

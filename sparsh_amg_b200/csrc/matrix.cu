@@ -1,0 +1,257 @@
+// matrix.cu — device CSR upload, kernel-family selection, and the per-op entry points of the C-ABI.
+// Replaces class sp_matrix_gpu (reference include/AMG_gpu_matrix.hpp:10-48, src/AMG_gpu_matrix.cu:26-142).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "internal.cuh"
+
+using namespace sparsh;
+
+namespace {
+
+// Row statistics drive the kernel family (spmv.cu).  Computed on the host from the arrays being uploaded.
+void choose_kernel(sparsh_matrix_s *A, const int *rp) {
+    const int n = A->nrow;
+    int max_row = 0, w128 = 0, w256 = 0;
+    for (int i = 0; i < n; i++) {
+        max_row = std::max(max_row, rp[i + 1] - rp[i]);
+        w128 = std::max(w128, rp[std::min(i + 128, n)] - rp[i]);
+        w256 = std::max(w256, rp[std::min(i + 256, n)] - rp[i]);
+    }
+    A->max_row = max_row;
+    A->win128 = w128;
+    A->win256 = w256;
+    A->mean_row = n > 0 ? (double)A->nnz / n : 0.0;
+    const double mean = A->mean_row;
+    // lanes for the vector family: smallest power of two >= mean/2, in [2,32]
+    int lanes = 2;
+    while (lanes < 32 && lanes * 2 <= mean) lanes *= 2;
+    A->lanes = lanes;
+    A->threads = mean <= 12.0 ? 256 : 128;
+    const int win = A->threads == 256 ? w256 : w128;
+    A->smem_bytes = (((win + 8) + 3) & ~3) * 12;
+    if (mean <= 2.5 && max_row <= 8) {
+        A->kind = KIND_SCALAR;
+        A->threads = 256;
+    } else if (A->smem_bytes <= 96 * 1024 && max_row <= 8 * mean + 16) {
+        A->kind = KIND_STREAM;  // >= 2 CTAs per SM, rows regular enough for thread-per-row
+    } else {
+        A->kind = KIND_VECTOR;
+    }
+}
+
+int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, const double *diag) {
+    Context &c = ctx();
+    const int n = A->nrow, nnz = A->nnz;
+    // padding: the stream kernel's bulk copies round the slice [rowptr[r0], rowptr[r1]) outwards to multiples of 4
+    const size_t pad_nnz = (((size_t)nnz + 3) & ~(size_t)3) + 8;
+    SP_CUDA(cudaMalloc(&A->rowptr, sizeof(int) * ((size_t)n + 8)));
+    SP_CUDA(cudaMalloc(&A->col, sizeof(int) * pad_nnz));
+    SP_CUDA(cudaMalloc(&A->val, sizeof(double) * pad_nnz));
+    SP_CUDA(cudaMemsetAsync(A->col + (nnz & ~3), 0, sizeof(int) * (pad_nnz - (size_t)(nnz & ~3)), c.stream));
+    SP_CUDA(cudaMemsetAsync(A->val + (nnz & ~3), 0, sizeof(double) * (pad_nnz - (size_t)(nnz & ~3)), c.stream));
+    SP_CUDA(cudaMemcpyAsync(A->rowptr, rp, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, c.stream));
+    if (nnz > 0) {
+        SP_CUDA(cudaMemcpyAsync(A->col, ci, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c.stream));
+        SP_CUDA(cudaMemcpyAsync(A->val, v, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c.stream));
+    }
+    std::vector<double> dtmp;
+    if (A->nrow == A->ncol) {
+        if (!diag) {
+            // sp_matrix_fill_diagonal (reference src/AMG_cpu_matrix.cpp:35-51): first stored entry with col == row
+            dtmp.assign((size_t)n, 0.0);
+            for (int i = 0; i < n; i++)
+                for (int j = rp[i]; j < rp[i + 1]; j++)
+                    if (ci[j] == i) {
+                        dtmp[i] = v[j];
+                        break;
+                    }
+            diag = dtmp.data();
+        }
+        SP_CUDA(cudaMalloc(&A->diag, sizeof(double) * ((size_t)n + 1)));
+        SP_CUDA(cudaMemcpyAsync(A->diag, diag, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    }
+    SP_CUDA(cudaStreamSynchronize(c.stream));  // host arrays may be pageable / temporary
+    return SPARSH_OK;
+}
+
+int validate(int nrow, int ncol, int nnz, const int *rp, const int *ci) {
+    SP_REQUIRE(nrow >= 0 && ncol >= 0 && nnz >= 0, "negative matrix dimension");
+    SP_REQUIRE(rp != nullptr, "rowptr is NULL");
+    SP_REQUIRE(rp[0] == 0 && rp[nrow] == nnz, "rowptr[0] != 0 or rowptr[nrow] != nnz");
+    for (int i = 0; i < nrow; i++) SP_REQUIRE(rp[i] <= rp[i + 1], "rowptr not monotone");
+    for (int j = 0; j < nnz; j++) SP_REQUIRE(ci[j] >= 0 && ci[j] < ncol, "column index out of range");
+    return SPARSH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex,
+                         const double *h_val, const double *h_diag, sparsh_matrix_t *out) {
+    SP_TRY(ensure_init());
+    SP_REQUIRE(out != nullptr, "out is NULL");
+    SP_TRY(validate(nrow, ncol, nnz, h_rowptr, h_colindex));
+    sparsh_matrix_s *A = new sparsh_matrix_s();
+    A->nrow = nrow;
+    A->ncol = ncol;
+    A->nnz = nnz;
+    choose_kernel(A, h_rowptr);
+    int rc = upload(A, h_rowptr, h_colindex, h_val, h_diag);
+    if (rc != SPARSH_OK) {
+        sparsh_matrix_destroy(A);
+        return rc;
+    }
+    *out = A;
+    return SPARSH_OK;
+}
+
+int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *rp, const int *ci, const double *v,
+                                   sparsh_matrix_t *out) {
+    SP_TRY(ensure_init());
+    SP_TRY(validate(nrow, ncol, nnz, rp, ci));
+    // stable counting sort: row c of the transpose lists the source rows in ascending order, which is the order
+    // in which the reference's transposed product scatters into b_c[c] (src/AMG_cycle_utilities.cpp:102)
+    std::vector<int> trp((size_t)ncol + 1, 0), tci((size_t)std::max(nnz, 1));
+    std::vector<double> tv((size_t)std::max(nnz, 1));
+    for (int j = 0; j < nnz; j++) trp[ci[j] + 1]++;
+    for (int c = 0; c < ncol; c++) trp[c + 1] += trp[c];
+    std::vector<int> cur(trp.begin(), trp.end() - 1);
+    for (int i = 0; i < nrow; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            int d = cur[ci[j]]++;
+            tci[d] = i;
+            tv[d] = v[j];
+        }
+    return sparsh_matrix_create(ncol, nrow, nnz, trp.data(), tci.data(), tv.data(), nullptr, out);
+}
+
+int sparsh_matrix_destroy(sparsh_matrix_t A) {
+    if (!A) return SPARSH_OK;
+    cudaFree(A->rowptr);
+    cudaFree(A->col);
+    cudaFree(A->val);
+    cudaFree(A->diag);
+    delete A;
+    return SPARSH_OK;
+}
+
+int sparsh_matrix_dims(sparsh_matrix_t A, int *nrow, int *ncol, int *nnz) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    if (nrow) *nrow = A->nrow;
+    if (ncol) *ncol = A->ncol;
+    if (nnz) *nnz = A->nnz;
+    return SPARSH_OK;
+}
+
+int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, int *smem_bytes) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    if (kind) *kind = A->kind;
+    if (threads_or_lanes) *threads_or_lanes = A->kind == KIND_VECTOR ? A->lanes : A->threads;
+    if (smem_bytes) *smem_bytes = A->kind == KIND_STREAM ? A->smem_bytes : 0;
+    return SPARSH_OK;
+}
+
+int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int tl) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    if (kind == KIND_SCALAR) {
+        A->kind = kind;
+        A->threads = 256;
+    } else if (kind == KIND_STREAM) {
+        SP_REQUIRE(tl == 128 || tl == 256, "stream kernel: threads must be 128 or 256");
+        const int win = tl == 256 ? A->win256 : A->win128;
+        const int smem = (((win + 8) + 3) & ~3) * 12;
+        SP_REQUIRE(smem <= 200 * 1024, "stream kernel: row window does not fit in shared memory");
+        A->kind = kind;
+        A->threads = tl;
+        A->smem_bytes = smem;
+    } else if (kind == KIND_VECTOR) {
+        SP_REQUIRE(tl == 2 || tl == 4 || tl == 8 || tl == 16 || tl == 32, "vector kernel: lanes must be 2..32");
+        A->kind = kind;
+        A->lanes = tl;
+    } else {
+        SP_REQUIRE(false, "unknown kernel kind");
+    }
+    return SPARSH_OK;
+}
+
+// ---- per-op entry points -------------------------------------------------------------------------------------
+int sparsh_spmv(sparsh_matrix_t A, const double *d_x, double *d_y) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    return launch_csr(A, EPI_SPMV, d_x, d_y, EpiArgs(), 0, A->nrow);
+}
+
+int sparsh_spmv_dot(sparsh_matrix_t A, const double *d_x, double *d_y, double *d_dot) {
+    SP_REQUIRE(A != nullptr && A->nrow == A->ncol, "spmv_dot needs a square matrix");
+    EpiArgs a;
+    a.xi = d_x;
+    a.red_out = d_dot;
+    return launch_csr(A, EPI_SPMV_DOT, d_x, d_y, a, 0, A->nrow);
+}
+
+int sparsh_residual(sparsh_matrix_t A, const double *d_b, const double *d_x, double *d_r) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    EpiArgs a;
+    a.b = d_b;
+    return launch_csr(A, EPI_RESID, d_x, d_r, a, 0, A->nrow);
+}
+
+int sparsh_residual_norm(sparsh_matrix_t A, const double *d_b, const double *d_x, double *h_norm) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    Context &c = ctx();
+    EpiArgs a;
+    a.b = d_b;
+    a.red_out = c.d_scalar;
+    SP_TRY(launch_csr(A, EPI_RESNORM, d_x, nullptr, a, 0, A->nrow));
+    SP_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    SP_CUDA(cudaStreamSynchronize(c.stream));
+    *h_norm = std::sqrt(c.h_scalar[0]);
+    return SPARSH_OK;
+}
+
+int sparsh_jacobi(sparsh_matrix_t A, const double *d_b, double *d_x, double *d_tmp, double omega, int sweeps) {
+    SP_REQUIRE(A != nullptr && A->diag != nullptr, "jacobi needs a square matrix with a diagonal");
+    SP_REQUIRE(sweeps >= 0, "negative sweep count");
+    double *cur = d_x, *other = d_tmp;
+    for (int s = 0; s < sweeps; s++) {
+        EpiArgs a;
+        a.b = d_b;
+        a.xi = cur;
+        a.d = A->diag;
+        a.omega = omega;
+        SP_TRY(launch_csr(A, EPI_JACOBI, cur, other, a, 0, A->nrow));
+        std::swap(cur, other);
+    }
+    if (cur != d_x) SP_CUDA(cudaMemcpyAsync(d_x, cur, sizeof(double) * (size_t)A->nrow, cudaMemcpyDeviceToDevice, ctx().stream));
+    return SPARSH_OK;
+}
+
+int sparsh_mc_sor(sparsh_matrix_t A, const int *h_color_count, int total_colors, const double *d_b, double *d_x,
+                  double omega, int sweeps) {
+    SP_REQUIRE(A != nullptr && A->diag != nullptr, "mc_sor needs a square matrix with a diagonal");
+    SP_REQUIRE(h_color_count != nullptr && total_colors >= 0, "bad colour table");
+    SP_REQUIRE(h_color_count[0] == 0 && h_color_count[total_colors] == A->nrow, "colour offsets do not cover the rows");
+    for (int s = 0; s < sweeps; s++)
+        for (int k = 0; k < total_colors; k++) {
+            EpiArgs a;
+            a.b = d_b;
+            a.d = A->diag;
+            a.omega = omega;
+            SP_TRY(launch_csr(A, EPI_SOR, d_x, d_x, a, h_color_count[k], h_color_count[k + 1]));
+        }
+    return SPARSH_OK;
+}
+
+int sparsh_restrict(sparsh_matrix_t R, const double *d_r, double *d_bc) {
+    SP_REQUIRE(R != nullptr, "matrix is NULL");
+    return launch_csr(R, EPI_SPMV, d_r, d_bc, EpiArgs(), 0, R->nrow);
+}
+
+int sparsh_prolong_add(sparsh_matrix_t P, const double *d_xc, double *d_xf) {
+    SP_REQUIRE(P != nullptr, "matrix is NULL");
+    return launch_csr(P, EPI_PROLONG, d_xc, d_xf, EpiArgs(), 0, P->nrow);
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// spmv.cu — the CSR row-sum kernel family of the AMG solve phase (K1-K6, K9 of SURVEY §8a).
+//
+// One templated row-sum  y_i = epilogue(sum_j a_ij x_j)  serves SpMV, fused residual, fused weighted-Jacobi
+// sweep, restriction (explicit R = P^T), fused prolongation-correction, one colour of multicolour SOR, and the
+// fused SpMV+dot / residual-norm reductions.  Three families, chosen per matrix at upload (matrix.cu):
+//
+//  * STREAM (the hot one, 4-32 nnz/row): one CTA owns THREADS consecutive rows.  One elected thread issues two
+//    TMA bulk copies (cp.async.bulk, SASS UBLKCP) that land the CTA's contiguous slice of `val` and `colindex`
+//    in shared memory, completion signalled on an mbarrier.  Then thread t walks row t left to right out of
+//    shared memory: the x gathers of neighbouring lanes hit neighbouring addresses (stencil rows), the matrix
+//    stream never touches the LSU/L1 path, and several CTAs per SM keep >100 KB of HBM traffic in flight.
+//    Row sums are accumulated sequentially with separate mul/add (no FMA contraction), i.e. in exactly the order
+//    of the reference's CPU path (mkl_sparse_d_mv over column-sorted rows): results are bit-identical to the
+//    oracle, not merely within 1e-12.
+//  * SCALAR (<= 2.5 nnz/row: aggregation P and R): thread per row straight from global memory (already coalesced).
+//  * VECTOR (irregular / long rows): 2..32 lanes per row, shuffle-tree reduction (1e-12 parity, not bit-exact).
+#include "internal.cuh"
+
+namespace sparsh {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy global -> shared
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SPARSH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SPARSH_DONE;\n"
+        "bra SPARSH_WAIT;\n"
+        "SPARSH_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogues.  Arithmetic and evaluation order follow the reference's CPU path:
+//   store_residual   r = b - (A x)                              src/AMG_cycle_utilities.cpp:120-121
+//   jacobi           x += (omega*(b - A x))/d                   src/AMG_smoothers.cpp:62-71
+//   transfer_solution xf = (P xc) + xf                          src/AMG_cycle_utilities.cpp:111
+//   sor (one colour) x -= (omega*((A x) - b))/d                 src/AMG_smoothers.cpp:90-98
+//   residual         ||(A x) - b||                              src/AMG_cycle_utilities.cpp:88-92
+// ---------------------------------------------------------------------------------------------------------
+struct EpiRegs {
+    double b, xi, d;
+};
+
+template <int EPI>
+__device__ __forceinline__ EpiRegs epi_load(const EpiArgs &a, const double *y, int row) {
+    EpiRegs e;
+    e.b = 0.0;
+    e.xi = 0.0;
+    e.d = 1.0;
+    if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM) e.b = a.b[row];
+    if (EPI == EPI_JACOBI || EPI == EPI_SPMV_DOT) e.xi = a.xi[row];
+    if (EPI == EPI_PROLONG || EPI == EPI_SOR) e.xi = y[row];
+    if (EPI == EPI_JACOBI || EPI == EPI_SOR) e.d = a.d[row];
+    return e;
+}
+
+// returns this row's contribution to the fused reduction (0 when the epilogue has none)
+template <int EPI>
+__device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, double s, double *y, int row) {
+    if (EPI == EPI_SPMV) {
+        y[row] = s;
+    } else if (EPI == EPI_RESID) {
+        y[row] = __dsub_rn(e.b, s);
+    } else if (EPI == EPI_JACOBI) {
+        double h = __dsub_rn(e.b, s);
+        y[row] = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
+    } else if (EPI == EPI_PROLONG) {
+        y[row] = __dadd_rn(s, e.xi);
+    } else if (EPI == EPI_SOR) {
+        double h = __dsub_rn(s, e.b);
+        y[row] = __dsub_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
+    } else if (EPI == EPI_SPMV_DOT) {
+        y[row] = s;
+        return __dmul_rn(e.xi, s);
+    } else if (EPI == EPI_RESNORM) {
+        double h = __dsub_rn(s, e.b);
+        return __dmul_rn(h, h);
+    }
+    return 0.0;
+}
+
+template <int EPI>
+struct EpiTraits {
+    static constexpr bool reduces = (EPI == EPI_SPMV_DOT || EPI == EPI_RESNORM);
+    // multicolour SOR updates x in place: its gathers must not use the non-coherent path
+    static constexpr bool coherent_x = (EPI == EPI_SOR);
+};
+
+template <bool COHERENT>
+__device__ __forceinline__ double load_x(const double *x, int c) {
+    if (COHERENT) return x[c];
+    return __ldg(x + c);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Deterministic two-stage reduction: fixed shuffle tree per block, block partials to global memory, the last
+// block to arrive (atomic ticket) adds the partials in index order.  The result does not depend on which block
+// finishes last, so it is bit-reproducible run to run.
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *sred) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();  // sred may still be read from a previous call
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < THREADS / 32) ? sred[threadIdx.x] : 0.0;
+    if (warp == 0) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    }
+    return v;  // valid in thread 0
+}
+
+template <int THREADS>
+__device__ __forceinline__ void grid_reduce_finalize(double contrib, double *partials, unsigned int *ticket,
+                                                     double *out) {
+    __shared__ double sred[32];
+    __shared__ int s_last;
+    double v = block_sum<THREADS>(contrib, sred);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double acc = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) acc += __ldcg(partials + i);
+        acc = block_sum<THREADS>(acc, sred);
+        if (threadIdx.x == 0) {
+            *out = acc;
+            *ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// STREAM kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS, int EPI>
+__global__ void __launch_bounds__(THREADS)
+    csr_stream_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end, int cap,
+                      double *partials, unsigned int *ticket) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(double));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_a0;
+
+    const int tid = threadIdx.x;
+    const int r0 = row_begin + blockIdx.x * THREADS;
+    const int nrows = min(THREADS, row_end - r0);
+
+    if (tid == 0) {
+        const int nz0 = A.rowptr[r0], nz1 = A.rowptr[r0 + nrows];
+        const int a0 = nz0 & ~3;         // val + a0 is 32-byte, col + a0 16-byte aligned
+        const int a1 = (nz1 + 3) & ~3;   // arrays are padded past nnz (matrix.cu)
+        const int cnt = a1 - a0;
+        s_a0 = a0;
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        if (cnt > 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)cnt * 12u);
+            bulk_g2s(sval, A.val + a0, (uint32_t)cnt * 8u, &bar);
+            bulk_g2s(scol, A.col + a0, (uint32_t)cnt * 4u, &bar);
+        } else {
+            mbar_arrive(&bar);
+        }
+    }
+    // per-row operands are fetched while the bulk copies are in flight
+    int lo = 0, hi = 0;
+    EpiRegs e;
+    const int row = r0 + tid;
+    const bool active = tid < nrows;
+    if (active) {
+        lo = A.rowptr[row];
+        hi = A.rowptr[row + 1];
+        e = epi_load<EPI>(args, y, row);
+    }
+    __syncthreads();  // barrier init and s_a0 visible to everyone
+    mbar_wait(&bar, 0);
+
+    double contrib = 0.0;
+    if (active) {
+        const int a0 = s_a0;
+        double s = 0.0;
+        for (int k = lo - a0; k < hi - a0; k += 8) {
+            double v[8], xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ok = k + j < hi - a0;
+                v[j] = ok ? sval[k + j] : 0.0;
+                const int c = ok ? scol[k + j] : 0;
+                xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (k + j < hi - a0) s = __dadd_rn(s, __dmul_rn(v[j], xv[j]));
+        }
+        contrib = epi_store<EPI>(args, e, s, y, row);
+    }
+    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<THREADS>(contrib, partials, ticket, args.red_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SCALAR kernel: thread per row, rows of 1-2 entries (aggregation P / R): global loads are already coalesced
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS, int EPI>
+__global__ void __launch_bounds__(THREADS)
+    csr_scalar_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end,
+                      double *partials, unsigned int *ticket) {
+    const int row = row_begin + blockIdx.x * THREADS + threadIdx.x;
+    double contrib = 0.0;
+    if (row < row_end) {
+        const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
+        EpiRegs e = epi_load<EPI>(args, y, row);
+        double s = 0.0;
+        for (int k = lo; k < hi; k++)
+            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
+        contrib = epi_store<EPI>(args, e, s, y, row);
+    }
+    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<THREADS>(contrib, partials, ticket, args.red_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// VECTOR kernel: LANES lanes per row, fixed shuffle tree
+// ---------------------------------------------------------------------------------------------------------
+template <int LANES, int EPI>
+__global__ void __launch_bounds__(256)
+    csr_vector_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end,
+                      double *partials, unsigned int *ticket) {
+    constexpr int ROWS_PER_CTA = 256 / LANES;
+    const int lane = threadIdx.x % LANES;
+    const int row = row_begin + blockIdx.x * ROWS_PER_CTA + threadIdx.x / LANES;
+    const bool active = row < row_end;
+    double s = 0.0;
+    EpiRegs e;
+    if (active) {
+        const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
+        if (lane == 0) e = epi_load<EPI>(args, y, row);
+        for (int k = lo + lane; k < hi; k += LANES)
+            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
+    }
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LANES);
+    double contrib = 0.0;
+    if (active && lane == 0) contrib = epi_store<EPI>(args, e, s, y, row);
+    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<256>(contrib, partials, ticket, args.red_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS, int EPI>
+static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+    Context &c = ctx();
+    static bool attr_set = false;
+    if (!attr_set) {
+        SP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<THREADS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+        attr_set = true;
+    }
+    const int win = THREADS == 256 ? A->win256 : A->win128;
+    const int cap = ((win + 8) + 3) & ~3;
+    const size_t smem = (size_t)cap * 12;
+    const int grid = (re - rb + THREADS - 1) / THREADS;
+    if (grid > RED_MAX_BLOCKS) {
+        set_error("matrix too large for the reduction workspace");
+        return SPARSH_ERR_INVALID;
+    }
+    csr_stream_kernel<THREADS, EPI><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, rb, re, cap, c.partials,
+                                                                      c.ticket);
+    count_launch();
+    SP_CUDA(cudaGetLastError());
+    return SPARSH_OK;
+}
+
+template <int EPI>
+static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+    Context &c = ctx();
+    const int grid = (re - rb + 255) / 256;
+    if (grid > RED_MAX_BLOCKS) {
+        set_error("matrix too large for the reduction workspace");
+        return SPARSH_ERR_INVALID;
+    }
+    csr_scalar_kernel<256, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, rb, re, c.partials, c.ticket);
+    count_launch();
+    SP_CUDA(cudaGetLastError());
+    return SPARSH_OK;
+}
+
+template <int LANES, int EPI>
+static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+    Context &c = ctx();
+    constexpr int ROWS = 256 / LANES;
+    const long long grid = ((long long)(re - rb) + ROWS - 1) / ROWS;
+    if (grid > RED_MAX_BLOCKS && EpiTraits<EPI>::reduces) {
+        set_error("matrix too large for the reduction workspace");
+        return SPARSH_ERR_INVALID;
+    }
+    csr_vector_kernel<LANES, EPI><<<(unsigned)grid, 256, 0, c.stream>>>(A->view(), x, y, args, rb, re, c.partials,
+                                                                        c.ticket);
+    count_launch();
+    SP_CUDA(cudaGetLastError());
+    return SPARSH_OK;
+}
+
+template <int EPI>
+static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+    if (re <= rb) {
+        if (EpiTraits<EPI>::reduces) SP_CUDA(cudaMemsetAsync(args.red_out, 0, sizeof(double), ctx().stream));
+        return SPARSH_OK;
+    }
+    switch (A->kind) {
+        case KIND_SCALAR:
+            return launch_scalar<EPI>(A, x, y, args, rb, re);
+        case KIND_STREAM:
+            return A->threads == 128 ? launch_stream<128, EPI>(A, x, y, args, rb, re)
+                                     : launch_stream<256, EPI>(A, x, y, args, rb, re);
+        default:
+            switch (A->lanes) {
+                case 2:
+                    return launch_vector<2, EPI>(A, x, y, args, rb, re);
+                case 4:
+                    return launch_vector<4, EPI>(A, x, y, args, rb, re);
+                case 8:
+                    return launch_vector<8, EPI>(A, x, y, args, rb, re);
+                case 16:
+                    return launch_vector<16, EPI>(A, x, y, args, rb, re);
+                default:
+                    return launch_vector<32, EPI>(A, x, y, args, rb, re);
+            }
+    }
+}
+
+int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
+               int row_end) {
+    switch (epi) {
+        case EPI_SPMV:
+            return launch_epi<EPI_SPMV>(A, x, y, args, row_begin, row_end);
+        case EPI_RESID:
+            return launch_epi<EPI_RESID>(A, x, y, args, row_begin, row_end);
+        case EPI_JACOBI:
+            return launch_epi<EPI_JACOBI>(A, x, y, args, row_begin, row_end);
+        case EPI_PROLONG:
+            return launch_epi<EPI_PROLONG>(A, x, y, args, row_begin, row_end);
+        case EPI_SOR:
+            return launch_epi<EPI_SOR>(A, x, y, args, row_begin, row_end);
+        case EPI_SPMV_DOT:
+            return launch_epi<EPI_SPMV_DOT>(A, x, y, args, row_begin, row_end);
+        case EPI_RESNORM:
+            return launch_epi<EPI_RESNORM>(A, x, y, args, row_begin, row_end);
+    }
+    set_error("unknown epilogue");
+    return SPARSH_ERR_INVALID;
+}
+
+}  // namespace sparsh

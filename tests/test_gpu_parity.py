@@ -1,0 +1,335 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs and against the golden vectors produced by the reference itself.
+
+Tolerances (north_star): per-kernel fp64 results within 1e-12 relative — the thread-per-row kernel families (stream,
+scalar) accumulate in the reference's order and must in fact be BIT-IDENTICAL; V-cycle / PCG residual histories within
+1e-10 relative with the same iteration count (+-1); integer data bit-exact.
+"""
+import numpy as np
+import pytest
+from conftest import system_by_name
+from oracle_bindings import CSR, OracleAmg
+
+pytestmark = pytest.mark.gpu
+
+OMEGA = 0.66667
+KINDS = [("scalar", 0, 256), ("stream", 1, 256), ("stream", 1, 128), ("vector", 2, 2), ("vector", 2, 8),
+         ("vector", 2, 32)]
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import sparsh_amg_b200 as s
+
+    s.init(0)  # raises (no fallback) if the extension or the GPU is missing
+    return s
+
+
+@pytest.fixture(scope="module")
+def fixture_hierarchies(oracle, fixture_system):
+    A, b = fixture_system
+    return {c: OracleAmg(A, coarsening=i) for i, c in enumerate(["hem", "beck"])}
+
+
+def rel_close(got, want, rtol):
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * max(1e-300, float(np.max(np.abs(want)))))
+
+
+def assert_hist(got, want, rtol=1e-10):
+    got, want = np.asarray(got), np.asarray(want)
+    assert abs(len(got) - len(want)) <= 1, (len(got), len(want))
+    m = min(len(got), len(want))
+    np.testing.assert_allclose(got[:m], want[:m], rtol=rtol, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------- per-op
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+@pytest.mark.parametrize("kname,kind,tl", KINDS)
+def test_level_ops_match_oracle(sp, oracle, fixture_hierarchies, coarsening, kname, kind, tl):
+    """K1-K5, K9 on every level of the fixture hierarchy, every kernel family."""
+    H = fixture_hierarchies[coarsening].hierarchy()
+    rng = np.random.default_rng(5)
+    exact = kname in ("scalar", "stream")
+    for L in H.levels:
+        A, diag = L["A"], L["diag"]
+        dA = sp.DeviceMatrix.from_csr(A, diag=diag).force_kernel(kind, tl)
+        x, b = rng.standard_normal(A.nrow), rng.standard_normal(A.nrow)
+        dx, db = sp.DeviceVector(data=x), sp.DeviceVector(data=b)
+        checks = [
+            (dA.spmv(dx).download(), oracle.spmv(A, x)),
+            (dA.residual(db, dx).download(), oracle.store_residual(A, b, x)),
+            (dA.jacobi(db, sp.DeviceVector(data=x), OMEGA, 7).download(), oracle.jacobi(A, diag, b, x, OMEGA, 6)),
+            (dA.jacobi(db, sp.DeviceVector(data=x), OMEGA, 2).download(), oracle.jacobi(A, diag, b, x, OMEGA, 1)),
+        ]
+        y, pdot = dA.spmv_dot(dx)
+        checks.append((y.download(), oracle.spmv(A, x)))
+        for got, want in checks:
+            if exact:
+                np.testing.assert_array_equal(got, want)
+            else:
+                rel_close(got, want, 1e-12)
+        np.testing.assert_allclose(pdot, np.dot(x, oracle.spmv(A, x)), rtol=1e-12)
+        np.testing.assert_allclose(dA.residual_norm(db, dx), oracle.residual(A, b, x), rtol=1e-12)
+        if L["P"] is not None:
+            P = L["P"]
+            xc = rng.standard_normal(P.ncol)
+            dP = sp.DeviceMatrix.from_csr(P).force_kernel(kind, tl)
+            dR = sp.DeviceMatrix.from_csr(P, transpose=True).force_kernel(kind, tl)
+            got_r = dR.restrict(dx).download()
+            got_p = dP.prolong_add(sp.DeviceVector(data=xc), sp.DeviceVector(data=x)).download()
+            if exact:
+                np.testing.assert_array_equal(got_r, oracle.transfer_residual(P, x))
+                np.testing.assert_array_equal(got_p, oracle.transfer_solution(P, xc, x))
+            else:
+                rel_close(got_r, oracle.transfer_residual(P, x), 1e-12)
+                rel_close(got_p, oracle.transfer_solution(P, xc, x), 1e-12)
+
+
+def test_default_kernel_selection(sp, oracle):
+    A = oracle.gen_poisson3d(20, 20, 20)
+    assert sp.DeviceMatrix.from_csr(A).kernel()[0] == sp.capi.KIND_STREAM
+    nc, agg = oracle.hem(A, 0)
+    P = CSR(A.nrow, nc, np.arange(A.nrow + 1, dtype=np.int32), agg, np.ones(A.nrow))
+    assert sp.DeviceMatrix.from_csr(P).kernel()[0] == sp.capi.KIND_SCALAR
+    assert sp.DeviceMatrix.from_csr(P, transpose=True).kernel()[0] == sp.capi.KIND_SCALAR
+    # one dense row among short ones -> irregular -> vector family
+    n = 600
+    rp = np.concatenate([[0], np.cumsum([n] + [1] * (n - 1))]).astype(np.int32)
+    ci = np.concatenate([np.arange(n), np.arange(1, n)]).astype(np.int32)
+    M = CSR(n, n, rp, ci, np.ones(len(ci)))
+    dM = sp.DeviceMatrix.from_csr(M)
+    assert dM.kernel()[0] == sp.capi.KIND_VECTOR
+    x = np.random.default_rng(1).standard_normal(n)
+    rel_close(dM.spmv(sp.DeviceVector(data=x)).download(), oracle.spmv(M, x), 1e-12)
+
+
+def test_edge_cases(sp, oracle):
+    # 1x1
+    A = CSR(1, 1, [0, 1], [0], [2.0])
+    assert sp.DeviceMatrix.from_csr(A).spmv(sp.DeviceVector(data=[3.0])).download()[0] == 6.0
+    # ragged with empty rows, all families
+    rng = np.random.default_rng(2)
+    n = 1000
+    lens = rng.integers(0, 9, n)
+    lens[::7] = 0
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+    M = CSR(n, n, rp, ci, rng.standard_normal(len(ci)))
+    x = rng.standard_normal(n)
+    want = oracle.spmv(M, x)
+    for kname, kind, tl in KINDS:
+        got = sp.DeviceMatrix.from_csr(M).force_kernel(kind, tl).spmv(sp.DeviceVector(data=x)).download()
+        if kname == "vector":
+            rel_close(got, want, 1e-12)
+        else:
+            np.testing.assert_array_equal(got, want)
+    # row counts that are not multiples of the CTA tile
+    for nx in (1, 5, 129, 257):
+        A = oracle.gen_poisson2d(nx, 3)
+        x = rng.standard_normal(A.nrow)
+        np.testing.assert_array_equal(sp.DeviceMatrix.from_csr(A).spmv(sp.DeviceVector(data=x)).download(),
+                                      oracle.spmv(A, x))
+    # invalid input is an error, not a crash
+    with pytest.raises(sp.SparshError):
+        sp.DeviceMatrix(2, 2, [0, 1, 2], [0, 5], [1.0, 1.0])
+
+
+def test_blas1(sp):
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 1000, 1 << 20, (1 << 20) + 3):
+        x, y, z = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+        dx, dy, dz = sp.DeviceVector(data=x), sp.DeviceVector(data=y), sp.DeviceVector(data=z)
+        np.testing.assert_allclose(sp.dot(dx, dy), np.dot(x, y), rtol=1e-12, atol=1e-12 * np.sqrt(n))
+        np.testing.assert_allclose(sp.nrm2(dx), np.linalg.norm(x), rtol=1e-13)
+        assert sp.dot(dx, dy) == sp.dot(dx, dy)  # fixed reduction tree: bit-reproducible
+        sp.axpy(0.37, dx, dy)
+        y = y + 0.37 * x
+        np.testing.assert_array_equal(dy.download(), y)
+        sp.axpby(1.5, dx, -0.25, dy)
+        y = 1.5 * x + (-0.25) * y
+        np.testing.assert_array_equal(dy.download(), y)
+        sp.axpbypcz(0.1, dx, 0.2, dy, 0.3, dz)
+        z = (0.1 * x + 0.2 * y) + 0.3 * z
+        np.testing.assert_array_equal(dz.download(), z)
+        np.testing.assert_array_equal(sp.DeviceVector(n).fill(2.5).download(), np.full(n, 2.5))
+
+
+def test_multicolour_sor(sp, oracle, fixture_system, golden):
+    """K6: colour-permuted system from the reference's colouring (integers bit-exact, checked in the CPU suite)."""
+    A, b = fixture_system
+    nc, perm, cc, Q = oracle.color_reorder(A)
+    qd = Q.diagonal()
+    dQ = sp.DeviceMatrix.from_csr(Q, diag=qd)
+    bp = b[perm]
+    want = oracle.sor_multicolor(Q, qd, cc, bp, np.zeros(A.nrow), OMEGA, 3)
+    got = dQ.mc_sor(cc, sp.DeviceVector(data=bp), sp.DeviceVector(data=np.zeros(A.nrow)), OMEGA, 3).download()
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(got[:8], golden["fixture"]["sor_probe"]["x_head"], rtol=1e-12)
+    # judged by iteration count: sweeps to reach ||Ax-b|| <= 1e-6 must match the oracle's
+    def sweeps_to(tol, step):
+        x = np.zeros(A.nrow)
+        for k in range(1, 400):
+            x = step(x)
+            if oracle.residual(Q, bp, x) <= tol:
+                return k
+        return -1
+    dx, db = sp.DeviceVector(A.nrow), sp.DeviceVector(data=bp)
+    def gpu_step(x):
+        dx.upload(x)
+        return dQ.mc_sor(cc, db, dx, OMEGA, 1).download()
+    k_gpu = sweeps_to(1e-6, gpu_step)
+    k_cpu = sweeps_to(1e-6, lambda x: oracle.sor_multicolor(Q, qd, cc, bp, x, OMEGA, 1))
+    assert k_gpu == k_cpu and k_gpu > 0
+
+
+# ------------------------------------------------------------------------------------------------ hierarchy
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_coarse_solve(sp, oracle, fixture_hierarchies, coarsening):
+    amg = fixture_hierarchies[coarsening]
+    H = amg.hierarchy()
+    dH = sp.DeviceHierarchy(H.levels)
+    n = H.levels[-1]["A"].nrow
+    b = np.random.default_rng(9).standard_normal(n)
+    got = dH.coarse_solve(sp.DeviceVector(data=b)).download()
+    want = amg.coarse_solve(b)
+    rel_close(got, want, 1e-10)
+    # and it really solves the system
+    r = b - H.levels[-1]["A"].to_scipy() @ got
+    assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b) * 1e3
+
+
+CASES = ["fixture", "poisson3d_24_ones", "poisson3d_24_axstar", "poisson2d_96_ones", "poisson2d_96_axstar"]
+
+
+@pytest.mark.parametrize("case", CASES + ["poisson3d_40_ones"])
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_vcycle_amg_pcg_against_reference_goldens(sp, oracle, fixture_system, golden, case, coarsening):
+    A, b = system_by_name(case, oracle, fixture_system)
+    g = golden[case][coarsening]
+    amg = OracleAmg(A, coarsening=0 if coarsening == "hem" else 1)
+    dH = sp.DeviceHierarchy(amg.hierarchy().levels)
+    db = sp.DeviceVector(data=b)
+    # one V-cycle from a seeded random start (AMG_solve_jacobi(b,x,1))
+    xr = np.random.default_rng(g["vcycle_probe"]["seed"]).random(A.nrow)
+    x1 = dH.vcycle(db, sp.DeviceVector(data=xr), 1).download()
+    np.testing.assert_allclose(x1[:8], g["vcycle_probe"]["x_head"], rtol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(x1), g["vcycle_probe"]["x_norm"], rtol=1e-10)
+    rel_close(x1, amg.vcycle(b, xr, 1), 1e-10)
+    # AMG as solver, absolute 1e-8 as the reference (AMG_Solver_CPU_baseline / AMG_Solver_CPU_GPU_MI)
+    dx = sp.DeviceVector(A.nrow).fill(0.0)
+    it, hist, ok = dH.amg_solve(db, dx, 1e-8)
+    assert ok
+    assert_hist(hist[1:], g["amg_solve_hist"])
+    np.testing.assert_allclose(hist[0], golden[case]["b_norm"], rtol=1e-12)
+    # AMG-PCG (Solver_PCG_1 semantics behind Solver_PCG_4)
+    dx.fill(0.0)
+    it, hist, ok = dH.pcg(db, dx, 1e-8)
+    assert ok
+    assert_hist(hist, g["pcg_hist"])
+    x = dx.download()
+    assert np.linalg.norm(b - A.to_scipy() @ x) <= 2e-8
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_shipped_entry_point_histories(sp, oracle, fixture_system, golden, case):
+    """HEM as shipped: AMG_Solver_CPU_baseline, Solver_PCG_1, Solver_PBiCG_1 histories from the reference's prints."""
+    A, b = system_by_name(case, oracle, fixture_system)
+    g = golden[case]
+    dH = sp.DeviceHierarchy(OracleAmg(A).hierarchy().levels)
+    db, dx = sp.DeviceVector(data=b), sp.DeviceVector(A.nrow)
+    it, hist, ok = dH.amg_solve(db, dx.fill(0.0), 1e-8)
+    assert_hist(hist[1:], g["AMG_Solver_CPU_baseline"]["hist"])
+    it, hist, ok = dH.pcg(db, dx.fill(0.0), 1e-8)
+    assert_hist(hist[1:], g["Solver_PCG_1"]["hist"])
+    np.testing.assert_allclose(np.linalg.norm(dx.download()), g["Solver_PCG_1"]["x_norm"], rtol=1e-9)
+    it, hist, ok = dH.pbicgstab(db, dx.fill(0.0), 1e-8)
+    assert ok
+    assert_hist(hist[1:], g["Solver_PBiCG_1"]["hist"], rtol=1e-8)  # BiCGStab amplifies rounding; counts must still match
+
+
+def test_fixture_headline_counts_on_gpu(sp, oracle, fixture_system):
+    """30 V-cycles, 13 PCG iterations, 7 PBiCGStab iterations on the bundled matrix."""
+    A, b = fixture_system
+    dH = sp.DeviceHierarchy(OracleAmg(A).hierarchy().levels)
+    db, dx = sp.DeviceVector(data=b), sp.DeviceVector(A.nrow)
+    assert dH.amg_solve(db, dx.fill(0.0), 1e-8)[0] == 30
+    assert dH.pcg(db, dx.fill(0.0), 1e-8)[0] == 13
+    assert dH.pbicgstab(db, dx.fill(0.0), 1e-8)[0] == 7
+
+
+def test_unpreconditioned_krylov(sp, fixture_system, golden):
+    A, b = fixture_system
+    dA = sp.DeviceMatrix.from_csr(A)
+    db, dx = sp.DeviceVector(data=b), sp.DeviceVector(A.nrow)
+    for fn, key in [(dA.cg, "Solver_CG_1"), (dA.bicgstab, "Solver_BiCG_1")]:
+        it, hist, ok = fn(db, dx.fill(0.0), 1e-8, 2000)
+        g = golden["fixture"][key]
+        assert ok and abs(it - g["iters"]) <= max(1, g["iters"] // 20)
+        np.testing.assert_allclose(hist[1:6], g["head"], rtol=1e-9)
+        assert np.linalg.norm(b - A.to_scipy() @ dx.download()) <= 1e-7
+
+
+def test_graph_and_direct_launch_agree_bitwise(sp, oracle, fixture_system):
+    A, b = fixture_system
+    levels = OracleAmg(A).hierarchy().levels
+    db = sp.DeviceVector(data=b)
+    out = []
+    for use_graph in (False, True):
+        dH = sp.DeviceHierarchy(levels, use_graph=use_graph)
+        dx = sp.DeviceVector(A.nrow).fill(0.0)
+        it, hist, ok = dH.pcg(db, dx, 1e-8)
+        out.append((it, hist.copy(), dx.download()))
+        dx.fill(0.0)
+        it2, hist2, _ = dH.pcg(db, dx, 1e-8)  # second solve on the same handle replays cached graphs
+        assert it2 == it and np.array_equal(hist2, hist)
+    assert out[0][0] == out[1][0]
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+
+
+def test_sweep_count_and_zero_guess_semantics(sp, oracle, fixture_system):
+    """6 sweeps = the reference GPU path's count; x_is_zero must equal an explicit zero vector."""
+    A, b = fixture_system
+    amg = OracleAmg(A)
+    levels = amg.hierarchy().levels
+    amg.set_smoother(OMEGA, 5)  # oracle runs smooth_iter+1 = 6 sweeps
+    dH = sp.DeviceHierarchy(levels, pre_sweeps=6, post_sweeps=6)
+    db = sp.DeviceVector(data=b)
+    x_a = dH.vcycle(db, sp.DeviceVector(A.nrow).fill(0.0), 1, x_is_zero=False).download()
+    x_b = dH.vcycle(db, sp.DeviceVector(A.nrow).fill(123.0), 1, x_is_zero=True).download()
+    np.testing.assert_array_equal(x_a, x_b)
+    rel_close(x_a, amg.vcycle(b, np.zeros(A.nrow), 1), 1e-10)
+    it, hist, ok = dH.amg_solve(db, sp.DeviceVector(A.nrow).fill(0.0), 1e-8)
+    assert it == 31  # SURVEY Appendix C, 6-sweep column
+
+
+def test_host_buffer_entry_point(sp, oracle, fixture_system, golden):
+    A, b = fixture_system
+    dH = sp.DeviceHierarchy(OracleAmg(A).hierarchy().levels)
+    x = np.zeros(A.nrow)
+    it, hist, ok = dH.solve_host("pcg", b, x, 1e-8)
+    assert ok and it == 13
+    assert np.linalg.norm(b - A.to_scipy() @ x) <= 2e-8
+    assert sp.launch_count() > 0
+
+
+# ------------------------------------------------------------------------ larger sizes: size-independent properties
+def test_properties_at_scale(sp, oracle):
+    """3D 7-point 96^3 (885k rows): linearity, A*1 = row sums, Jacobi fixed point, PCG true residual."""
+    nx = 96
+    A = oracle.gen_poisson3d(nx, nx, nx)
+    n = A.nrow
+    dA = sp.DeviceMatrix.from_csr(A)
+    rng = np.random.default_rng(4)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    dx, dy = sp.DeviceVector(data=x), sp.DeviceVector(data=y)
+    ones = dA.spmv(sp.DeviceVector(n).fill(1.0)).download()
+    rowsum = np.add.reduceat(A.val, A.rowptr[:-1])
+    np.testing.assert_array_equal(ones, rowsum)
+    np.testing.assert_array_equal(dA.spmv(dx).download(), oracle.spmv(A, x))
+    lhs = dA.spmv(sp.DeviceVector(data=2.0 * x + y)).download()
+    rel_close(lhs, 2.0 * dA.spmv(dx).download() + dA.spmv(dy).download(), 1e-13)
+    b = oracle.spmv(A, x)
+    fixed = dA.jacobi(sp.DeviceVector(data=b), sp.DeviceVector(data=x), OMEGA, 3).download()
+    rel_close(fixed, x, 1e-13)
+    assert dA.residual_norm(sp.DeviceVector(data=b), dx) <= 1e-10 * np.linalg.norm(b)
