@@ -123,6 +123,10 @@ typedef struct {
     int p_ncol, p_nnz;
     const int *p_rowptr, *p_colindex;
     const double *p_val;
+    /* multicolour smoother only (params.smoother == 1): A_l is colour-permuted, rows color_count[k]..color_count[k+1]
+     * share colour k (sp_matrix_mg::color_count / total_colors, include/AMG_cpu_matrix.hpp:24-26).  NULL/0 otherwise. */
+    int total_colors;
+    const int *color_count;
 } sparsh_level_desc;
 
 typedef struct {
@@ -131,6 +135,9 @@ typedef struct {
     int post_sweeps;  /* Jacobi sweeps after prolongation                                        */
     int use_graph;    /* capture V-cycle / Krylov iterations into CUDA graphs (1) or launch directly (0) */
     int coarse_mode;  /* 0: dense inverse formed on the device at setup, applied as a GEMV (K7)  */
+    int smoother;     /* 0: weighted Jacobi (AMG_solve_jacobi, src/AMG_phases.cpp:151-230)
+                         1: multicolour SOR  (AMG_solve_SOR,   src/AMG_phases.cpp:234-306); pre/post_sweeps then count
+                            SOR sweeps (the reference hard-codes 6, src/AMG_phases.cpp:251,265) */
 } sparsh_params;
 void sparsh_params_default(sparsh_params *p);
 

@@ -26,12 +26,12 @@ class SparshError(RuntimeError):
 class LevelDesc(C.Structure):
     _fields_ = [("nrow", C.c_int), ("nnz", C.c_int), ("rowptr", c_int_p), ("colindex", c_int_p), ("val", c_dbl_p),
                 ("diag", c_dbl_p), ("p_ncol", C.c_int), ("p_nnz", C.c_int), ("p_rowptr", c_int_p),
-                ("p_colindex", c_int_p), ("p_val", c_dbl_p)]
+                ("p_colindex", c_int_p), ("p_val", c_dbl_p), ("total_colors", C.c_int), ("color_count", c_int_p)]
 
 
 class Params(C.Structure):
     _fields_ = [("omega", C.c_double), ("pre_sweeps", C.c_int), ("post_sweeps", C.c_int), ("use_graph", C.c_int),
-                ("coarse_mode", C.c_int)]
+                ("coarse_mode", C.c_int), ("smoother", C.c_int)]
 
 
 # every symbol include/sparsh_b200.h declares: (restype, argtypes)

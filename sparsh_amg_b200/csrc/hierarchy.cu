@@ -21,8 +21,18 @@ namespace sparsh {
 
 static int smooth(sparsh_hierarchy_s *h, Level &L, const double *b, double *&cur, double *&other, int sweeps,
                   bool zero_guess) {
-    if (sweeps == 0) {
+    if (sweeps == 0 || h->prm.smoother == 1) {
         if (zero_guess) SP_TRY(k_fill(cur, (size_t)L.n, 0.0));
+        // multicolour SOR, in place, one launch per colour (reference src/AMG_smoothers.cpp:78-102)
+        const int ncol = (int)L.color_count.size() - 1;
+        for (int s = 0; s < sweeps && h->prm.smoother == 1; s++)
+            for (int k = 0; k < ncol; k++) {
+                EpiArgs a;
+                a.b = b;
+                a.d = L.A->diag;
+                a.omega = h->prm.omega;
+                SP_TRY(launch_csr(L.A, EPI_SOR, cur, cur, a, L.color_count[k], L.color_count[k + 1]));
+            }
         return SPARSH_OK;
     }
     for (int s = 0; s < sweeps; s++) {
@@ -91,6 +101,7 @@ void sparsh_params_default(sparsh_params *p) {
     p->post_sweeps = 7;
     p->use_graph = 1;
     p->coarse_mode = 0;
+    p->smoother = 0;
 }
 
 int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const sparsh_params *params,
@@ -114,6 +125,14 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
         if (cudaMalloc(&L.tbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
         if (l > 0 && rc == SPARSH_OK) {
             if (cudaMalloc(&L.xbuf, bytes) != cudaSuccess || cudaMalloc(&L.bbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
+        }
+        if (h->prm.smoother == 1 && l < nlevels - 1 && rc == SPARSH_OK) {
+            if (!d.color_count || d.total_colors < 1 || d.color_count[0] != 0 || d.color_count[d.total_colors] != d.nrow) {
+                set_error("multicolour smoother: level lacks a valid colour table");
+                rc = SPARSH_ERR_INVALID;
+                break;
+            }
+            L.color_count.assign(d.color_count, d.color_count + d.total_colors + 1);
         }
         if (l < nlevels - 1 && rc == SPARSH_OK) {
             if (d.p_rowptr == nullptr || d.p_ncol != levels[l + 1].nrow) {

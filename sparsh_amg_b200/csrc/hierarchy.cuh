@@ -17,6 +17,7 @@ struct Level {
     double *tbuf = nullptr;  // Jacobi ping-pong partner
     double *bbuf = nullptr;  // right-hand side (levels >= 1)
     double *rbuf = nullptr;  // residual        (all but the coarsest)
+    std::vector<int> color_count;  // multicolour smoother: prefix offsets per colour (host copy)
 };
 
 struct GraphEntry {

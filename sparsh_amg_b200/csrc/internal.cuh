@@ -58,7 +58,7 @@ inline void count_launch() {
         c.launches++;
 }
 
-constexpr int RED_MAX_BLOCKS = 1 << 18;  // enough for 2^26 rows at 256 rows per block
+constexpr int RED_MAX_BLOCKS = 1 << 20;  // partial sums per reduced value (2^28 rows at 256 rows per block)
 constexpr int RED_MAX_VALUES = 4;
 
 // ---- device CSR ---------------------------------------------------------------------------------------

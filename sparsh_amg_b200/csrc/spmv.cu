@@ -120,9 +120,8 @@ __device__ __forceinline__ double load_x(const double *x, int c) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Deterministic two-stage reduction: fixed shuffle tree per block, block partials to global memory, the last
-// block to arrive (atomic ticket) adds the partials in index order.  The result does not depend on which block
-// finishes last, so it is bit-reproducible run to run.
+// Deterministic two-stage reduction: fixed shuffle tree per block, block partials to global memory, then one CTA
+// adds the partials in index order.  The result does not depend on block scheduling: bit-reproducible run to run.
 // ---------------------------------------------------------------------------------------------------------
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double *sred) {
@@ -140,29 +139,22 @@ __device__ __forceinline__ double block_sum(double v, double *sred) {
     return v;  // valid in thread 0
 }
 
+// stage 1: one partial per block (fixed shuffle tree)
 template <int THREADS>
-__device__ __forceinline__ void grid_reduce_finalize(double contrib, double *partials, unsigned int *ticket,
-                                                     double *out) {
+__device__ __forceinline__ void block_partial(double contrib, double *partials) {
     __shared__ double sred[32];
-    __shared__ int s_last;
     double v = block_sum<THREADS>(contrib, sred);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = v;
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double acc = 0.0;
-        for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) acc += __ldcg(partials + i);
-        acc = block_sum<THREADS>(acc, sred);
-        if (threadIdx.x == 0) {
-            *out = acc;
-            *ticket = 0u;
-        }
-    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+
+// stage 2: a single CTA adds the partials in index order (65536 per-block atomics on one ticket cost ~60 us on a
+// 256^3 SpMV; this kernel costs ~4 us and keeps the result independent of block scheduling)
+__global__ void __launch_bounds__(1024) finalize_partials_kernel(const double *__restrict__ partials, int count, double *out) {
+    __shared__ double sred[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) acc += partials[i];
+    acc = block_sum<1024>(acc, sred);
+    if (threadIdx.x == 0) *out = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -230,7 +222,7 @@ __global__ void __launch_bounds__(THREADS)
         }
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
-    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<THREADS>(contrib, partials, ticket, args.red_out);
+    if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -250,7 +242,7 @@ __global__ void __launch_bounds__(THREADS)
             s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
-    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<THREADS>(contrib, partials, ticket, args.red_out);
+    if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -276,7 +268,7 @@ __global__ void __launch_bounds__(256)
     for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LANES);
     double contrib = 0.0;
     if (active && lane == 0) contrib = epi_store<EPI>(args, e, s, y, row);
-    if (EpiTraits<EPI>::reduces) grid_reduce_finalize<256>(contrib, partials, ticket, args.red_out);
+    if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -303,6 +295,11 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
                                                                       c.ticket);
     count_launch();
     SP_CUDA(cudaGetLastError());
+    if (EpiTraits<EPI>::reduces) {
+        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+    }
     return SPARSH_OK;
 }
 
@@ -317,6 +314,11 @@ static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, c
     csr_scalar_kernel<256, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, rb, re, c.partials, c.ticket);
     count_launch();
     SP_CUDA(cudaGetLastError());
+    if (EpiTraits<EPI>::reduces) {
+        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+    }
     return SPARSH_OK;
 }
 
@@ -325,7 +327,7 @@ static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, c
     Context &c = ctx();
     constexpr int ROWS = 256 / LANES;
     const long long grid = ((long long)(re - rb) + ROWS - 1) / ROWS;
-    if (grid > RED_MAX_BLOCKS && EpiTraits<EPI>::reduces) {
+    if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
@@ -333,6 +335,11 @@ static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, c
                                                                         c.ticket);
     count_launch();
     SP_CUDA(cudaGetLastError());
+    if (EpiTraits<EPI>::reduces) {
+        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+    }
     return SPARSH_OK;
 }
 

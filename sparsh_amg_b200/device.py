@@ -206,7 +206,7 @@ def axpbypcz(a, x, b, y, c, z):
 class DeviceHierarchy:
     """levels: list of dicts(A=CSR-like, diag=ndarray|None, P=CSR-like|None) with .nrow/.ncol/.rowptr/.colindex/.val"""
 
-    def __init__(self, levels, omega=0.66667, pre_sweeps=7, post_sweeps=7, use_graph=True):
+    def __init__(self, levels, omega=0.66667, pre_sweeps=7, post_sweeps=7, use_graph=True, smoother="jacobi"):
         self.lib = capi.load()
         n = len(levels)
         descs = (capi.LevelDesc * n)()
@@ -232,9 +232,14 @@ class DeviceHierarchy:
                 keep += [prp, pci, pv]
                 d.p_ncol, d.p_nnz = P.ncol, int(prp[-1])
                 d.p_rowptr, d.p_colindex, d.p_val = ip(prp), ip(pci), dp(pv)
+            if L.get("color_count") is not None:
+                cc = np.ascontiguousarray(L["color_count"], dtype=np.int32)
+                keep.append(cc)
+                d.total_colors, d.color_count = len(cc) - 1, ip(cc)
         prm = capi.Params()
         self.lib.sparsh_params_default(C.byref(prm))
         prm.omega, prm.pre_sweeps, prm.post_sweeps, prm.use_graph = omega, pre_sweeps, post_sweeps, int(use_graph)
+        prm.smoother = 1 if smoother == "sor" else 0
         h = C.c_void_p()
         check(self.lib.sparsh_hierarchy_create(n, descs, C.byref(prm), C.byref(h)))
         self.h = h.value

@@ -1,0 +1,444 @@
+// setup.cpp — matrices and the host setup phase (coarsening + Galerkin products) behind the reference's names.
+//
+// The solve phase is the product of this repository; the setup phase only has to hand it the same hierarchy the
+// reference would build.  These are native re-implementations (no MKL): integer outputs (aggregates, C/F splitting,
+// colour permutation, sparsity patterns) are bit-identical to the reference's, coarse values agree to rounding.
+//   sp_matrix / sp_matrix_mg            reference src/AMG_matrix.cpp:15-67, src/AMG_cpu_matrix.cpp:17-237
+//   sequential::HEM_Prolongator         reference src/AMG_coarsening.cpp:14-97
+//   sequential::beck_prolongator        reference src/AMG_coarsening.cpp:269-339
+//   parallel::coarsen_matrix            reference src/AMG_cycle_utilities.cpp:126-146
+//   AMG_solver::AMG_solver_setup_*      reference src/AMG_phases.cpp:35-147
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+#include <vector>
+
+#include "sparsh_amg.hpp"
+
+namespace sparsh {
+Options &options() {
+    static Options o;
+    return o;
+}
+Report &last_report() {
+    static Report r;
+    return r;
+}
+}  // namespace sparsh
+
+using sparsh::options;
+
+// ---------------------------------------------------------------------------------------------------------
+// sp_matrix / sp_matrix_mg
+// ---------------------------------------------------------------------------------------------------------
+sp_matrix::sp_matrix(int r, int c, int n) : nrow(r), ncol(c), nnz(n) {
+    rowptr = new int[(size_t)r + 1]();
+    colindex = new int[(size_t)(n > 0 ? n : 1)]();
+    val = new double[(size_t)(n > 0 ? n : 1)]();
+}
+sp_matrix::sp_matrix() {}
+
+void sp_matrix::check_sp_matrix() {
+    std::cout << "\n Number of Rows: " << nrow << "\n Number of columns " << ncol << "\n Number of non-zeros " << nnz
+              << std::endl;
+    for (int i = 0; i < nrow; i++) {
+        std::cout << i << std::endl;
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++) std::cout << colindex[j] << "\t" << val[j] << "\t" << std::endl;
+        std::cout << std::endl << std::endl;
+    }
+}
+
+static void sort_row(int len, int *c, double *v) {
+    if (len <= 32) {
+        for (int a = 1; a < len; a++) {
+            const int cc = c[a];
+            const double vv = v[a];
+            int b = a - 1;
+            while (b >= 0 && c[b] > cc) {
+                c[b + 1] = c[b];
+                v[b + 1] = v[b];
+                b--;
+            }
+            c[b + 1] = cc;
+            v[b + 1] = vv;
+        }
+        return;
+    }
+    std::vector<int> idx(len);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int p, int q) { return c[p] < c[q]; });
+    std::vector<int> cc(c, c + len);
+    std::vector<double> vv(v, v + len);
+    for (int k = 0; k < len; k++) {
+        c[k] = cc[idx[k]];
+        v[k] = vv[idx[k]];
+    }
+}
+
+static void sort_columns(int nrow, const int *rp, int *ci, double *v) {
+#pragma omp parallel for num_threads(options().threads) schedule(dynamic, 4096)
+    for (int i = 0; i < nrow; i++) sort_row(rp[i + 1] - rp[i], ci + rp[i], v + rp[i]);
+}
+
+// The reference wraps the arrays in an MKL handle and lets mkl_sparse_order sort each row's columns in place
+// (src/AMG_cpu_matrix.cpp:22-29); only the sort has an observable effect.
+void sp_matrix_mg::sp_matrix_fill() {
+    nnz = rowptr[nrow];
+    sort_columns(nrow, rowptr, colindex, val);
+}
+
+// src/AMG_cpu_matrix.cpp:35-51: first stored entry whose column equals the row
+void sp_matrix_mg::sp_matrix_fill_diagonal() {
+    delete[] diagonal;
+    delete[] helper;
+    diagonal = new double[(size_t)nrow]();
+    helper = new double[(size_t)nrow]();
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int i = 0; i < nrow; i++)
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++)
+            if (colindex[j] == i) {
+                diagonal[i] = val[j];
+                break;
+            }
+}
+
+sp_matrix_mg::~sp_matrix_mg() {
+    // tolerate the reference's idiom of explicit destructor calls followed by nothing (main.cpp:40)
+    delete[] diagonal;
+    delete[] helper;
+    delete[] entries;
+    delete[] color;
+    delete[] color_count;
+    diagonal = helper = entries = nullptr;
+    color = color_count = nullptr;
+}
+
+// src/AMG_cpu_matrix.cpp:81-199: greedy first-fit colouring in natural order over the stored columns; `color` then
+// becomes perm[new] = old (grouped by colour, ascending inside a colour), color_count the prefix offsets, and the
+// matrix is permuted symmetrically in place.
+void sp_matrix_mg::color_matrix_and_reorder() {
+    const int n = nrow;
+    int max_count = 0;
+    for (int i = 0; i < n; i++) max_count = std::max(max_count, rowptr[i + 1] - rowptr[i]);
+    std::vector<int> col_of(n, 0), forbidden(max_count + 1, -1), cc(max_count + 1, 0);
+    total_colors = 0;
+    for (int i = 0; i < n; i++) {
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++)
+            if (col_of[colindex[j]] != 0) forbidden[col_of[colindex[j]]] = i;
+        int c = 0x7fffffff;
+        for (int k = 1; k < max_count + 1; k++)
+            if (forbidden[k] != i) {
+                c = k;
+                break;
+            }
+        col_of[i] = c;
+        cc[c]++;
+        total_colors = std::max(total_colors, c);
+    }
+    for (int k = 0; k < total_colors; k++) cc[k + 1] += cc[k];
+    delete[] color;
+    delete[] color_count;
+    color = new int[(size_t)n];
+    color_count = new int[(size_t)max_count + 1]();
+    std::vector<int> cur(total_colors + 1, 0);
+    for (int k = 1; k <= total_colors; k++) cur[k] = cc[k - 1];
+    for (int i = 0; i < n; i++) color[cur[col_of[i]]++] = i;
+    for (int k = 0; k <= total_colors; k++) color_count[k] = cc[k];
+
+    std::vector<int> inv(n);
+    for (int i = 0; i < n; i++) inv[color[i]] = i;
+    int *qrp = new int[(size_t)n + 1];
+    qrp[0] = 0;
+    for (int i = 0; i < n; i++) qrp[i + 1] = qrp[i] + (rowptr[color[i] + 1] - rowptr[color[i]]);
+    int *qci = new int[(size_t)std::max(qrp[n], 1)];
+    double *qv = new double[(size_t)std::max(qrp[n], 1)];
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int i = 0; i < n; i++) {
+        int o = qrp[i];
+        for (int j = rowptr[color[i]]; j < rowptr[color[i] + 1]; j++, o++) {
+            qci[o] = inv[colindex[j]];
+            qv[o] = val[j];
+        }
+    }
+    // the reference re-points rowptr/colindex/val at the product's arrays (and leaks the old ones); we own ours
+    delete[] rowptr;
+    delete[] colindex;
+    delete[] val;
+    rowptr = qrp;
+    colindex = qci;
+    val = qv;
+    sp_matrix_fill();
+    sp_matrix_fill_diagonal();
+}
+
+// src/AMG_cpu_matrix.cpp:203-219
+void sp_matrix_mg::normalize_matrix() {
+    std::vector<double> norm1(ncol, 0.0);
+    for (int i = 0; i < nrow; i++)
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++) norm1[colindex[j]] += val[j] * val[j];
+    for (int i = 0; i < nrow; i++)
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++) val[j] = val[j] / norm1[colindex[j]];
+}
+
+// src/AMG_cpu_matrix.cpp:223-237
+void sp_matrix_mg::scale_system(double *&b) {
+    for (int i = 0; i < nrow; i++) {
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++) val[j] = val[j] / diagonal[i];
+        b[i] = b[i] / std::sqrt(diagonal[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// coarsening
+// ---------------------------------------------------------------------------------------------------------
+namespace sequential {
+
+// Heavy-edge matching.  Forward sweep on even levels, backward on odd ones; a free row pairs with its free neighbour of
+// strictly largest |a_ij| (ties: first in column order; zeros never); leftovers become singletons numbered last.
+// P is n x n_coarse with a single 1.0 per row.  The greedy sweep is inherently sequential, O(nnz).
+void HEM_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int l1) {
+    const int n = A.nrow;
+    P = new sp_matrix_mg(n, 1, n);
+    int *agg = P->colindex;
+    std::fill(agg, agg + n, -1);
+    std::fill(P->val, P->val + n, 1.0);
+    int next_id = 0;
+    const int first = (l1 % 2 == 0) ? 0 : n - 1, step = (l1 % 2 == 0) ? 1 : -1;
+    for (int t = 0, i = first; t < n; t++, i += step) {
+        if (agg[i] != -1) continue;
+        int mate = -1;
+        double heaviest = 0.0;
+        for (int j = A.rowptr[i]; j < A.rowptr[i + 1]; j++) {
+            const int c = A.colindex[j];
+            const double w = std::fabs(A.val[j]);
+            if (agg[c] == -1 && w > heaviest && c != i) {
+                heaviest = w;
+                mate = c;
+            }
+        }
+        if (mate != -1) {
+            agg[i] = next_id;
+            agg[mate] = next_id;
+            next_id++;
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (agg[i] == -1) agg[i] = next_id++;
+    for (int i = 0; i <= n; i++) P->rowptr[i] = i;
+    P->ncol = next_id;
+    P->nnz = n;
+}
+
+// Beck's classical coarsening: first-fit C-point selection in natural order (a row still at 0 becomes a C point and
+// decrements every stored neighbour); C rows are identity rows, an F row averages its C neighbours with weight
+// 1/|c_f[i]|.  Columns sorted per row.
+void beck_prolongator(sp_matrix_mg &A, sp_matrix_mg *&P1) {
+    const int n = A.nrow;
+    std::vector<int> cf(n, 0);
+    int ncoarse = 0;
+    for (int i = 0; i < n; i++) {
+        if (cf[i] != 0) continue;
+        for (int j = A.rowptr[i]; j < A.rowptr[i + 1]; j++) cf[A.colindex[j]] -= 1;
+        cf[i] = ++ncoarse;
+    }
+    std::vector<int> rp(n + 1, 0);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int i = 0; i < n; i++) {
+        int cnt = 0;
+        if (cf[i] > 0)
+            cnt = 1;
+        else if (cf[i] < 0)
+            for (int j = A.rowptr[i]; j < A.rowptr[i + 1]; j++) cnt += cf[A.colindex[j]] > 0;
+        rp[i + 1] = cnt;
+    }
+    for (int i = 0; i < n; i++) rp[i + 1] += rp[i];
+    P1 = new sp_matrix_mg(n, ncoarse, rp[n]);
+    std::copy(rp.begin(), rp.end(), P1->rowptr);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int i = 0; i < n; i++) {
+        int o = rp[i];
+        if (cf[i] > 0) {
+            P1->colindex[o] = cf[i] - 1;
+            P1->val[o] = 1.0;
+        } else if (cf[i] < 0) {
+            const double w = 1 / std::fabs((double)cf[i]);
+            for (int j = A.rowptr[i]; j < A.rowptr[i + 1]; j++) {
+                const int k = A.colindex[j];
+                if (cf[k] > 0) {
+                    P1->colindex[o] = cf[k] - 1;
+                    P1->val[o] = w;
+                    o++;
+                }
+            }
+        }
+    }
+    P1->sp_matrix_fill();
+}
+
+}  // namespace sequential
+
+// ---------------------------------------------------------------------------------------------------------
+// Galerkin product
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Csr {
+    int nrow = 0, ncol = 0;
+    std::vector<int> rp, ci;
+    std::vector<double> v;
+};
+
+// row-wise (Gustavson) C = A * B with a dense position table per thread; the entries of a C row appear in first-touch
+// order and each is accumulated in traversal order, which fixes the rounding independently of the thread count
+void spgemm(int arow, const int *arp, const int *aci, const double *av, int bcol, const int *brp, const int *bci,
+            const double *bv, Csr &C) {
+    C.nrow = arow;
+    C.ncol = bcol;
+    C.rp.assign((size_t)arow + 1, 0);
+    const int nt = options().threads;
+#pragma omp parallel num_threads(nt)
+    {
+        std::vector<int> mark((size_t)std::max(bcol, 1), -1);
+#pragma omp for schedule(dynamic, 4096)
+        for (int i = 0; i < arow; i++) {
+            int cnt = 0;
+            for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+                const int k = aci[ja];
+                for (int jb = brp[k]; jb < brp[k + 1]; jb++)
+                    if (mark[bci[jb]] != i) {
+                        mark[bci[jb]] = i;
+                        cnt++;
+                    }
+            }
+            C.rp[i + 1] = cnt;
+        }
+    }
+    for (int i = 0; i < arow; i++) C.rp[i + 1] += C.rp[i];
+    C.ci.resize((size_t)std::max(C.rp[arow], 1));
+    C.v.resize((size_t)std::max(C.rp[arow], 1));
+#pragma omp parallel num_threads(nt)
+    {
+        std::vector<int> pos((size_t)std::max(bcol, 1), -1);
+#pragma omp for schedule(dynamic, 4096)
+        for (int i = 0; i < arow; i++) {
+            const int base = C.rp[i];
+            int o = base;
+            for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+                const int k = aci[ja];
+                const double a = av[ja];
+                for (int jb = brp[k]; jb < brp[k + 1]; jb++) {
+                    const int c = bci[jb];
+                    if (pos[c] < base) {
+                        pos[c] = o;
+                        C.ci[o] = c;
+                        C.v[o] = a * bv[jb];
+                        o++;
+                    } else {
+                        C.v[pos[c]] += a * bv[jb];
+                    }
+                }
+            }
+        }
+    }
+}
+
+void transpose(int nrow, int ncol, const int *rp, const int *ci, const double *v, Csr &T) {
+    const int nnz = rp[nrow];
+    T.nrow = ncol;
+    T.ncol = nrow;
+    T.rp.assign((size_t)ncol + 1, 0);
+    T.ci.resize((size_t)std::max(nnz, 1));
+    T.v.resize((size_t)std::max(nnz, 1));
+    for (int j = 0; j < nnz; j++) T.rp[ci[j] + 1]++;
+    for (int c = 0; c < ncol; c++) T.rp[c + 1] += T.rp[c];
+    std::vector<int> cur(T.rp.begin(), T.rp.end() - 1);
+    for (int i = 0; i < nrow; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int d = cur[ci[j]]++;
+            T.ci[d] = i;
+            T.v[d] = v[j];
+        }
+}
+
+}  // namespace
+
+namespace parallel {
+
+// Ac = P^T (A P), columns sorted, diagonal extracted
+void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
+    Csr AP, R, C;
+    spgemm(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, AP);
+    transpose(P1.nrow, P1.ncol, P1.rowptr, P1.colindex, P1.val, R);
+    spgemm(R.nrow, R.rp.data(), R.ci.data(), R.v.data(), P1.ncol, AP.rp.data(), AP.ci.data(), AP.v.data(), C);
+    const int nc = P1.ncol, cnnz = C.rp[nc];
+    Ac = new sp_matrix_mg(nc, nc, cnnz);
+    std::copy(C.rp.begin(), C.rp.end(), Ac->rowptr);
+    std::copy(C.ci.begin(), C.ci.begin() + cnnz, Ac->colindex);
+    std::copy(C.v.begin(), C.v.begin() + cnnz, Ac->val);
+    Ac->sp_matrix_fill();
+    Ac->sp_matrix_fill_diagonal();
+}
+
+// reference src/AMG_cycle_utilities.cpp:149-188: the columns of P follow the coarse matrix' colour permutation,
+// P <- P * Pt^T with Pt[new, perm[new]] = 1, i.e. column c becomes inv[c]
+void reorder_prolongator(sp_matrix_mg &A, sp_matrix_mg *&P) {
+    std::vector<int> inv(A.nrow);
+    for (int i = 0; i < A.nrow; i++) inv[A.color[i]] = i;
+    for (int j = 0; j < P->rowptr[P->nrow]; j++) P->colindex[j] = inv[P->colindex[j]];
+    P->sp_matrix_fill();
+}
+
+// reference src/AMG_cycle_utilities.cpp:191-223: b <- Pt b, b_new[i] = b[perm[i]]
+void reorder_rhs(sp_matrix_mg &A, double *&b) {
+    std::vector<double> t(A.nrow);
+    for (int i = 0; i < A.nrow; i++) t[i] = b[A.color[i]];
+    std::copy(t.begin(), t.end(), b);
+}
+
+}  // namespace parallel
+
+// ---------------------------------------------------------------------------------------------------------
+// AMG_solver: hierarchy construction
+// ---------------------------------------------------------------------------------------------------------
+AMG_solver::AMG_solver() {
+    const int cap = std::max(options().max_levels, 1);
+    Av = new sp_matrix_mg *[cap]();
+    Pv = new sp_matrix_mg *[cap]();
+    Xv = new double *[cap]();
+    Bv = new double *[cap]();
+    Rv = new double *[cap]();
+}
+
+static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
+    const sparsh::Options &o = options();
+    const double t0 = omp_get_wtime();
+    S.l = 0;
+    S.Av[0] = &A;  // borrowed, as in the reference (src/AMG_phases.cpp:40)
+    if (o.print_setup) std::cout << "AMG Setup Phase Details " << (colour ? "SOR Smoother" : "Jacobi smoother") << std::endl;
+    if (colour) S.Av[0]->color_matrix_and_reorder();
+    int l = 0;
+    while (S.Av[l]->nrow > o.coarse_upper && l < o.max_levels - 1) {
+        if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
+        if (o.coarsening == sparsh::COARSEN_BECK)
+            sequential::beck_prolongator(*S.Av[l], S.Pv[l]);
+        else
+            sequential::HEM_Prolongator(*S.Av[l], S.Pv[l], l);
+        parallel::coarsen_matrix(*S.Av[l], S.Av[l + 1], *S.Pv[l]);
+        if (colour) {
+            S.Av[l + 1]->color_matrix_and_reorder();
+            parallel::reorder_prolongator(*S.Av[l + 1], S.Pv[l]);
+        }
+        l++;
+        if (S.Av[l]->nrow < o.coarse_lower) break;
+    }
+    if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
+    S.l = l;
+    sparsh::last_report().setup_seconds = omp_get_wtime() - t0;
+}
+
+void AMG_solver::AMG_solver_setup_jacobi(sp_matrix_mg &A) { build_hierarchy(*this, A, false); }
+void AMG_solver::AMG_solver_setup_SOR(sp_matrix_mg &A) { build_hierarchy(*this, A, true); }

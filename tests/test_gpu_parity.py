@@ -165,20 +165,25 @@ def test_multicolour_sor(sp, oracle, fixture_system, golden):
     got = dQ.mc_sor(cc, sp.DeviceVector(data=bp), sp.DeviceVector(data=np.zeros(A.nrow)), OMEGA, 3).download()
     np.testing.assert_array_equal(got, want)
     np.testing.assert_allclose(got[:8], golden["fixture"]["sor_probe"]["x_head"], rtol=1e-12)
-    # judged by iteration count: sweeps to reach ||Ax-b|| <= 1e-6 must match the oracle's
-    def sweeps_to(tol, step):
+    # judged by iteration count (north_star): sweeps needed to cut ||Ax-b|| tenfold must match the oracle's
+    r_start = oracle.residual(Q, bp, np.zeros(A.nrow))
+
+    def sweeps_to(step):
         x = np.zeros(A.nrow)
-        for k in range(1, 400):
+        for k in range(1, 2000):
             x = step(x)
-            if oracle.residual(Q, bp, x) <= tol:
+            if oracle.residual(Q, bp, x) <= 0.1 * r_start:
                 return k
         return -1
+
     dx, db = sp.DeviceVector(A.nrow), sp.DeviceVector(data=bp)
+
     def gpu_step(x):
         dx.upload(x)
         return dQ.mc_sor(cc, db, dx, OMEGA, 1).download()
-    k_gpu = sweeps_to(1e-6, gpu_step)
-    k_cpu = sweeps_to(1e-6, lambda x: oracle.sor_multicolor(Q, qd, cc, bp, x, OMEGA, 1))
+
+    k_gpu = sweeps_to(gpu_step)
+    k_cpu = sweeps_to(lambda x: oracle.sor_multicolor(Q, qd, cc, bp, x, OMEGA, 1))
     assert k_gpu == k_cpu and k_gpu > 0
 
 

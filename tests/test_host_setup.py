@@ -1,0 +1,153 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/sparsh_b200.h
+declares (no compute without a GPU), and the native setup phase (HEM / Beck / Galerkin / colouring) reproduces the
+reference's hierarchy — integer data bit-exact, coarse values to rounding."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import ROOT, system_by_name
+from oracle_bindings import OracleAmg
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_cabi_exports_every_declared_symbol():
+    import sparsh_amg_b200 as sp
+
+    header = open(os.path.join(ROOT, "include", "sparsh_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sparsh_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 45
+    lib = sp.capi.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sparsh_b200.h but not exported"
+    assert declared == set(sp.capi.SIGNATURES), declared ^ set(sp.capi.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU the product must fail loudly, never compute on the CPU."""
+    import sparsh_amg_b200 as sp
+
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(sp.SparshError):
+        sp.init(0)
+    with pytest.raises(sp.SparshError):
+        sp.DeviceVector(data=np.ones(4))
+
+
+def test_product_does_not_touch_the_oracle():
+    """Only tests/, smoke() and bench.py may reach oracle/ — the package sources must not mention it."""
+    pkg = os.path.join(ROOT, "sparsh_amg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.sep + "build" in dirpath or dirpath.endswith("lib"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "sparsh_oracle" not in text and "oracle/" not in text and "libsparsh_ref" not in text, f
+
+
+@pytest.fixture(scope="module")
+def host():
+    from sparsh_amg_b200 import host as h
+
+    h.set_options(threads=min(8, os.cpu_count() or 1), max_levels=32, print_setup=0, print_solve=0)
+    return h
+
+
+CASES = ["fixture", "poisson3d_24_ones", "poisson2d_96_ones", "poisson3d_40_ones"]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("coarsening", ["hem", "beck"])
+def test_native_setup_matches_reference_hierarchy(host, oracle, fixture_system, golden, case, coarsening):
+    A, b = system_by_name(case, oracle, fixture_system)
+    host.set_options(coarsening=0 if coarsening == "hem" else 1)
+    M = host.HostMatrix.from_csr(A)
+    amg = host.HostAmg(M)
+    levels = amg.levels()
+    want = golden[case][coarsening]["levels"]
+    ref_levels = OracleAmg(A, coarsening=0 if coarsening == "hem" else 1).hierarchy().levels
+    assert len(levels) == len(want)
+    for L, w, R in zip(levels, want, ref_levels):
+        assert (L["A"].nrow, L["A"].nnz) == (w["nrow"], w["nnz"])
+        assert sha(L["A"].rowptr) == w["rowptr_sha"]          # integer data bit-exact vs the reference run
+        assert sha(L["A"].colindex) == w["colindex_sha"]
+        np.testing.assert_allclose(L["A"].val, R["A"].val, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(L["diag"], R["diag"], rtol=1e-13)
+        np.testing.assert_allclose(np.sum(L["A"].val), w["val_sum"], rtol=1e-12, atol=1e-9)
+        if L["P"] is not None:
+            assert (L["P"].ncol, L["P"].nnz) == (w["p_ncol"], w["p_nnz"])
+            assert sha(L["P"].rowptr) == w["p_rowptr_sha"]
+            assert sha(L["P"].colindex) == w["p_colindex_sha"]
+            np.testing.assert_array_equal(L["P"].val, R["P"].val)
+    amg.free()
+    M.free()
+    host.set_options(coarsening=0)
+
+
+def test_native_colouring_matches_reference(host, fixture_system, golden, oracle):
+    A, b = fixture_system
+    M = host.HostMatrix.from_csr(A)
+    nc, perm, cc = M.color_reorder()
+    g = golden["fixture"]["coloring"]
+    assert nc == g["total_colors"] and cc.tolist() == g["color_count"]
+    assert sha(perm) == g["perm_sha"]
+    assert sha(M.rowptr) == g["q_rowptr_sha"] and sha(M.colindex) == g["q_colindex_sha"]
+    np.testing.assert_allclose(np.sum(M.val), g["q_val_sum"], rtol=1e-13)
+    M.free()
+
+
+def test_generators_match_oracle_generators(host, oracle):
+    for (nx, ny, nz) in [(7, 5, 3), (16, 16, 16), (1, 1, 1)]:
+        M = host.HostMatrix.poisson3d(nx, ny, nz)
+        O = oracle.gen_poisson3d(nx, ny, nz)
+        assert np.array_equal(M.rowptr, O.rowptr) and np.array_equal(M.colindex, O.colindex)
+        assert np.array_equal(M.val, O.val)
+        M.free()
+    M = host.HostMatrix.poisson2d(33, 17)
+    O = oracle.gen_poisson2d(33, 17)
+    assert np.array_equal(M.rowptr, O.rowptr) and np.array_equal(M.colindex, O.colindex) and np.array_equal(M.val, O.val)
+    # SURVEY §8d nnz formulas: 2D 5n - 2(nx+ny), 3D 7n - 2(nx ny + ny nz + nx nz), 27-pt (3n-2)^3 for a cube
+    assert M.nnz == 5 * 33 * 17 - 2 * (33 + 17)
+    M.free()
+    D = host.HostMatrix.diffusion27(6, 6, 6)
+    assert D.nnz == (3 * 6 - 2) ** 3
+    S = D  # SPD-like checks: symmetric, positive diagonal, zero row sums only away from the Dirichlet boundary
+    import scipy.sparse as sps
+
+    T = sps.csr_matrix((S.val, S.colindex, S.rowptr), shape=(S.nrow, S.ncol))
+    assert abs(T - T.T).max() < 1e-12 * abs(T).max()
+    assert np.all(T.diagonal() > 0)
+    w = np.linalg.eigvalsh(T.toarray())
+    assert w.min() > 0
+    D.free()
+
+
+def test_reader_roundtrip(host, tmp_path, fixture_system):
+    A, b = fixture_system
+    n = 200  # leading principal block of the bundled matrix, written in the reference's two-file format
+    rp = A.rowptr[: n + 1]
+    keep = [(i, A.colindex[j], A.val[j]) for i in range(n) for j in range(rp[i], rp[i + 1]) if A.colindex[j] < n]
+    mf, rf = tmp_path / "m.txt", tmp_path / "rhs.txt"
+    with open(mf, "w") as f:
+        f.write(f"{n} {n} {len(keep)}\n")
+        for i, c, v in keep:
+            f.write(f"{i}\t{int(c)}\t{float(v)!r}\t\n")
+    with open(rf, "w") as f:
+        f.write(f"{n}\n" + "\n".join(repr(float(x)) for x in b[:n]) + "\n")
+    M, bb = host.HostMatrix.read(str(mf), str(rf))
+    assert (M.nrow, M.nnz) == (n, len(keep))
+    np.testing.assert_array_equal(bb, b[:n])
+    np.testing.assert_array_equal(M.val, [v for _, _, v in keep])
+    M.free()
