@@ -162,6 +162,36 @@ void *ref_amg_setup(int n, int nnz, const int *rp, const int *ci, const double *
     return h;
 }
 
+// Adopt an externally built hierarchy ("same hierarchy, built once, shared with the GPU path") so that
+// the CPU baseline can time the reference's own V-cycle / PCG loop at full size without repeating its sequential setup.
+// Arrays are copied into reference objects; the coarsest level gets the reference's Direct_Solver_Pardiso.
+void *ref_amg_from_levels(int nlevels, const int *nrow, const int *const *rp, const int *const *ci,
+                          const double *const *v, const int *pncol, const int *const *prp, const int *const *pci,
+                          const double *const *pv) {
+    CoutCapture cap;
+    RefAmg *h = new RefAmg();
+    AMG_solver *S = h->S = new AMG_solver();
+    for (int k = 0; k < nlevels; k++) {
+        S->Av[k] = make_matrix(nrow[k], rp[k][nrow[k]], rp[k], ci[k], v[k]);
+        S->Xv[k] = new double[nrow[k]]();
+        S->Bv[k] = new double[nrow[k]]();
+        S->Rv[k] = new double[nrow[k]]();
+        if (k < nlevels - 1) {
+            const int pn = prp[k][nrow[k]];
+            sp_matrix_mg *P = new sp_matrix_mg(nrow[k], pncol[k], pn);
+            std::memcpy(P->rowptr, prp[k], sizeof(int) * ((size_t)nrow[k] + 1));
+            std::memcpy(P->colindex, pci[k], sizeof(int) * (size_t)pn);
+            std::memcpy(P->val, pv[k], sizeof(double) * (size_t)pn);
+            P->sp_matrix_fill();
+            S->Pv[k] = P;
+        }
+    }
+    h->A = S->Av[0];
+    S->l = nlevels - 1;
+    S->Directsolve = new Direct_Solver_Pardiso(*S->Av[S->l]);
+    return h;
+}
+
 double ref_amg_setup_seconds(void *hv) { return ((RefAmg *)hv)->setup_seconds; }
 int ref_amg_nlevels(void *hv) { return ((RefAmg *)hv)->S->l + 1; }
 

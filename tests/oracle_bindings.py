@@ -324,6 +324,7 @@ class Ref:
         lib.ref_set_tol.argtypes = [C.c_double]
         lib.ref_set_tol_call_limit.argtypes = [C.c_long]
         lib.ref_amg_setup.restype = C.c_void_p
+        lib.ref_amg_from_levels.restype = C.c_void_p
         lib.ref_amg_setup_seconds.restype = C.c_double
         lib.ref_amg_setup_seconds.argtypes = [C.c_void_p]
         lib.ref_amg_nlevels.argtypes = [C.c_void_p]
@@ -380,10 +381,27 @@ class Ref:
 
 
 class RefAmg:
-    def __init__(self, A, coarsening=0):
+    def __init__(self, A=None, coarsening=0, levels=None):
         self.r = Ref.get()
-        self.h = self.r.lib.ref_amg_setup(A.nrow, A.nnz, ip(A.rowptr), ip(A.colindex), dp(A.val), coarsening)
-        self.n = A.nrow
+        if levels is None:
+            self.h = self.r.lib.ref_amg_setup(A.nrow, A.nnz, ip(A.rowptr), ip(A.colindex), dp(A.val), coarsening)
+            self.n = A.nrow
+        else:  # adopt an existing hierarchy: list of dict(A=..., P=...) with numpy arrays
+            n = len(levels)
+            nrow = (C.c_int * n)(*[l["A"].nrow for l in levels])
+            pncol = (C.c_int * n)(*[(l["P"].ncol if l["P"] is not None else 0) for l in levels])
+            null_i, null_d = C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+
+            def parr(getter, ctype):
+                return (C.POINTER(ctype) * n)(*[getter(l) for l in levels])
+
+            self.h = self.r.lib.ref_amg_from_levels(
+                n, nrow, parr(lambda l: ip(l["A"].rowptr), C.c_int), parr(lambda l: ip(l["A"].colindex), C.c_int),
+                parr(lambda l: dp(l["A"].val), C.c_double), pncol,
+                parr(lambda l: ip(l["P"].rowptr) if l["P"] is not None else null_i, C.c_int),
+                parr(lambda l: ip(l["P"].colindex) if l["P"] is not None else null_i, C.c_int),
+                parr(lambda l: dp(l["P"].val) if l["P"] is not None else null_d, C.c_double))
+            self.n = levels[0]["A"].nrow
 
     @property
     def nlevels(self):
