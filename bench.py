@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--ref-iters", type=int, default=2, help="PCG iterations per bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tail-threshold", type=int, default=300000,
+                    help="N>1: levels with at most this many rows are replicated on every GPU instead of partitioned")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: honour --warmup/--max-iter literally, do not insist on convergence")
     args = ap.parse_args()

@@ -184,6 +184,56 @@ int sparsh_hierarchy_solve_host(sparsh_hierarchy_t h, int method, const double *
 /* bytes moved by one V-cycle according to the algorithmic model of SURVEY §8d (for roofline reports) */
 double sparsh_hierarchy_vcycle_bytes(sparsh_hierarchy_t h, int x_is_zero);
 
+/* ------------------------------------------------------------------ multi-GPU -- */
+/* One process per GPU, NCCL over NVLink 5 / NVSwitch (the reference has no distributed path at all: SURVEY §2.1 last
+ * row; this is new work behind the same solver semantics).  Every level's A, P and R = P^T are row-partitioned;
+ * a rank stores its rows with columns relabelled to [owned | halo] positions (entry order inside a row is preserved, so
+ * row sums are bit-identical to the single-GPU ones).  Before an operator is applied, the halo part of its input vector
+ * is filled by grouped ncclSend/ncclRecv of packed boundary entries; Krylov scalars are combined with ncclAllReduce on
+ * 1-2 doubles.  Levels at and below a size threshold are gathered once per cycle (ncclAllGather) and solved redundantly
+ * on every GPU with the single-GPU hierarchy code. */
+#define SPARSH_NCCL_ID_BYTES 128
+int sparsh_dist_get_unique_id(char *id128);                        /* rank 0; the launcher broadcasts it */
+int sparsh_dist_init(const char *id128, int nranks, int rank);     /* ncclCommInitRank on the current device */
+int sparsh_dist_finalize(void);
+int sparsh_dist_info(int *nranks, int *rank);
+
+typedef struct {
+    int nrow;       /* owned rows of the operator's row space                                  */
+    int ncol_local; /* owned entries of its column-space vector                                */
+    int nhalo;      /* remote entries appended after them: input vectors are [owned | halo]    */
+    int nnz;
+    const int *rowptr, *colindex; /* local CSR, columns relabelled, entry order preserved      */
+    const double *val;
+    const double *diag;           /* A only (NULL for P, R)                                    */
+    int n_send;                   /* neighbours this rank sends to                             */
+    const int *send_rank, *send_ptr, *send_idx; /* send_ptr[n_send+1] into send_idx (owned positions to pack) */
+    int n_recv;                   /* neighbours it receives from                               */
+    const int *recv_rank, *recv_ptr;            /* recv_ptr[n_recv+1]: offsets inside the halo segment */
+    int interior_begin, interior_end;           /* rows [begin,end) reference no halo entry    */
+} sparsh_dist_op_desc;
+
+typedef struct {
+    sparsh_dist_op_desc A; /* level l                      */
+    sparsh_dist_op_desc P; /* level l rows x level l+1 cols */
+    sparsh_dist_op_desc R; /* level l+1 rows x level l cols */
+} sparsh_dist_level_desc;
+
+typedef struct sparsh_dist_s *sparsh_dist_t;
+/* lev[0..n_dist_levels) are distributed; tail[0..n_tail_levels) (global numbering, tail[0] = level n_dist_levels) are
+ * replicated.  tail_counts[r] = rows of tail[0] owned by rank r, tail_rows = their global ids, rank-major. */
+int sparsh_dist_hierarchy_create(int n_dist_levels, const sparsh_dist_level_desc *lev, int n_tail_levels,
+                                 const sparsh_level_desc *tail, const int *tail_counts, const int *tail_rows,
+                                 const sparsh_params *params, sparsh_dist_t *out);
+int sparsh_dist_hierarchy_destroy(sparsh_dist_t h);
+int sparsh_dist_local_rows(sparsh_dist_t h, int level, int *nrow);
+/* y_local = A_level x (x_local: owned entries only; the halo exchange happens inside) */
+int sparsh_dist_spmv(sparsh_dist_t h, int level, const double *d_x_local, double *d_y_local);
+int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_local, int cycles, int x_is_zero);
+/* distributed AMG-PCG: same arithmetic as sparsh_hierarchy_pcg, dots completed by ncclAllReduce */
+int sparsh_dist_pcg(sparsh_dist_t h, const double *d_b_local, double *d_x_local, double tol, int max_iter,
+                    double *h_hist, int *iters);
+
 #ifdef __cplusplus
 }
 #endif

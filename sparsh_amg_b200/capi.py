@@ -87,7 +87,27 @@ SIGNATURES = {
     "sparsh_bicgstab": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
     "sparsh_hierarchy_solve_host": (_i, [_vp, _i, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
     "sparsh_hierarchy_vcycle_bytes": (_d, [_vp, _i]),
+    # multi-GPU
+    "sparsh_dist_get_unique_id": (_i, [C.c_char_p]),
+    "sparsh_dist_init": (_i, [C.c_char_p, _i, _i]),
+    "sparsh_dist_finalize": (_i, []),
+    "sparsh_dist_info": (_i, [c_int_p, c_int_p]),
+    "sparsh_dist_hierarchy_create": (_i, [_i, _vp, _i, _vp, c_int_p, c_int_p, _vp, _vpp]),
+    "sparsh_dist_hierarchy_destroy": (_i, [_vp]),
+    "sparsh_dist_local_rows": (_i, [_vp, _i, c_int_p]),
+    "sparsh_dist_spmv": (_i, [_vp, _i, _vp, _vp]),
+    "sparsh_dist_vcycle": (_i, [_vp, _vp, _vp, _i, _i]),
+    "sparsh_dist_pcg": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
 }
+
+
+class DistOpDesc(C.Structure):
+    """sparsh_dist_op_desc (include/sparsh_b200.h)"""
+    _fields_ = [("nrow", C.c_int), ("ncol_local", C.c_int), ("nhalo", C.c_int), ("nnz", C.c_int),
+                ("rowptr", c_int_p), ("colindex", c_int_p), ("val", c_dbl_p), ("diag", c_dbl_p),
+                ("n_send", C.c_int), ("send_rank", c_int_p), ("send_ptr", c_int_p), ("send_idx", c_int_p),
+                ("n_recv", C.c_int), ("recv_rank", c_int_p), ("recv_ptr", c_int_p),
+                ("interior_begin", C.c_int), ("interior_end", C.c_int)]
 
 _lib = None
 

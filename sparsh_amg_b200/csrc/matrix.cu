@@ -57,7 +57,7 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
         SP_CUDA(cudaMemcpyAsync(A->val, v, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c.stream));
     }
     std::vector<double> dtmp;
-    if (A->nrow == A->ncol) {
+    if (A->nrow == A->ncol || diag) {
         if (!diag) {
             // sp_matrix_fill_diagonal (reference src/AMG_cpu_matrix.cpp:35-51): first stored entry with col == row
             dtmp.assign((size_t)n, 0.0);

@@ -1,0 +1,347 @@
+// dist_plan.cpp — host-side partitioning of a hierarchy for the multi-GPU solve phase.
+//
+// The reference is single-process; this is new.  Every rank holds the whole host hierarchy (the setup phase is
+// sequential host code anyway) and cuts out ITS part:
+//   * ownership: level 0 is split into contiguous, balanced row blocks; a coarse row belongs to the rank that owns the
+//     first fine row of its aggregate / its C point.  Inheriting ownership through P keeps restriction and prolongation
+//     almost entirely local and makes the reversed numbering of odd HEM levels (backward sweep, reference
+//     src/AMG_coarsening.cpp:56) a non-issue: blocks follow the grid, not the index.
+//   * local operators: rows in ascending global order, columns relabelled to [owned | halo] positions WITHOUT reordering
+//     the entries of a row, so device row sums are bit-identical to the single-GPU ones.
+//   * exchange plans: who sends which owned entries to whom, where received entries land in the halo segment.
+//   * levels with at most `tail_threshold` rows are not partitioned: they are replicated on every GPU.
+// The same arrays feed the device (sparsh_dist_hierarchy_create) and the CPU tests (gloo, world size 2).
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/sparsh_b200.h"
+#include "sparsh_amg.hpp"
+
+using sparsh::options;
+
+namespace {
+
+struct OpLocal {
+    int nrow = 0, ncol_local = 0, nhalo = 0;
+    std::vector<int> rp, ci;
+    std::vector<double> v, diag;
+    std::vector<int> send_rank, send_ptr, send_idx, recv_rank, recv_ptr;
+    std::vector<int> halo_global;  // global ids of the halo entries, in halo order (tests)
+    int ib = 0, ie = 0;
+    sparsh_dist_op_desc desc() const {
+        sparsh_dist_op_desc d;
+        std::memset(&d, 0, sizeof d);
+        d.nrow = nrow;
+        d.ncol_local = ncol_local;
+        d.nhalo = nhalo;
+        d.nnz = rp.empty() ? 0 : rp.back();
+        d.rowptr = rp.data();
+        d.colindex = ci.data();
+        d.val = v.data();
+        d.diag = diag.empty() ? nullptr : diag.data();
+        d.n_send = (int)send_rank.size();
+        d.send_rank = send_rank.data();
+        d.send_ptr = send_ptr.data();
+        d.send_idx = send_idx.data();
+        d.n_recv = (int)recv_rank.size();
+        d.recv_rank = recv_rank.data();
+        d.recv_ptr = recv_ptr.data();
+        d.interior_begin = ib;
+        d.interior_end = ie;
+        return d;
+    }
+};
+
+struct Space {                 // distribution of one level's index space
+    std::vector<int> owner;    // global id -> rank
+    std::vector<int> loc;      // global id -> position inside its owner's ascending list
+    std::vector<int> count;    // per rank
+};
+
+struct LevelLocal {
+    OpLocal A, P, R;
+    std::vector<int> rows;  // owned global ids of this level, ascending
+};
+
+struct DistPlan {
+    int nranks = 1, rank = 0, nd = 0, nlevels = 0;
+    std::vector<LevelLocal> lev;
+    std::vector<int> tail_counts, tail_rows, tail_rows_mine;
+    AMG_solver *S = nullptr;
+    sparsh_dist_t device = nullptr;
+};
+
+void finish_space(Space &s, int nranks) {
+    const int n = (int)s.owner.size();
+    s.loc.resize(n);
+    s.count.assign(nranks, 0);
+    for (int g = 0; g < n; g++) s.loc[g] = s.count[s.owner[g]]++;
+}
+
+// rows owned by `rank` of the global CSR (row space rs, column space cs) -> local operator + exchange plan
+void build_op(int nrow_g, const int *rp, const int *ci, const double *v, const double *diag, const Space &rs,
+              const Space &cs, int nranks, int rank, OpLocal &op) {
+    std::vector<int> rows;
+    rows.reserve(rs.count[rank]);
+    for (int g = 0; g < nrow_g; g++)
+        if (rs.owner[g] == rank) rows.push_back(g);
+    op.nrow = (int)rows.size();
+    op.ncol_local = cs.count[rank];
+    // halo = referenced columns owned elsewhere, ordered by (owner, global id)
+    std::vector<std::pair<int, int>> halo;
+    op.rp.assign((size_t)op.nrow + 1, 0);
+    for (int k = 0; k < op.nrow; k++) {
+        const int g = rows[k];
+        op.rp[k + 1] = op.rp[k] + (rp[g + 1] - rp[g]);
+        for (int j = rp[g]; j < rp[g + 1]; j++)
+            if (cs.owner[ci[j]] != rank) halo.emplace_back(cs.owner[ci[j]], ci[j]);
+    }
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    op.nhalo = (int)halo.size();
+    op.halo_global.resize(halo.size());
+    for (size_t h = 0; h < halo.size(); h++) op.halo_global[h] = halo[h].second;
+    for (size_t h = 0; h < halo.size();) {
+        size_t e = h;
+        while (e < halo.size() && halo[e].first == halo[h].first) e++;
+        op.recv_rank.push_back(halo[h].first);
+        op.recv_ptr.push_back((int)h);
+        h = e;
+    }
+    op.recv_ptr.push_back((int)halo.size());
+    // local CSR: same entries in the same order, columns relabelled
+    op.ci.resize((size_t)std::max(op.rp[op.nrow], 1));
+    op.v.resize((size_t)std::max(op.rp[op.nrow], 1));
+    if (diag) op.diag.resize((size_t)op.nrow);
+    std::vector<char> boundary((size_t)op.nrow, 0);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int k = 0; k < op.nrow; k++) {
+        const int g = rows[k];
+        int o = op.rp[k];
+        for (int j = rp[g]; j < rp[g + 1]; j++, o++) {
+            const int c = ci[j];
+            if (cs.owner[c] == rank) {
+                op.ci[o] = cs.loc[c];
+            } else {
+                const auto it = std::lower_bound(halo.begin(), halo.end(), std::make_pair(cs.owner[c], c));
+                op.ci[o] = op.ncol_local + (int)(it - halo.begin());
+                boundary[k] = 1;
+            }
+            op.v[o] = v[j];
+        }
+        if (diag) op.diag[k] = diag[g];
+    }
+    // longest run of rows that touch no halo entry: computed while the exchange is in flight
+    int best_b = 0, best_e = 0, run_b = 0;
+    for (int k = 0; k <= op.nrow; k++) {
+        if (k == op.nrow || boundary[k]) {
+            if (k - run_b > best_e - best_b) {
+                best_b = run_b;
+                best_e = k;
+            }
+            run_b = k + 1;
+        }
+    }
+    op.ib = best_b;
+    op.ie = best_e;
+    // what the others need from me: columns I own that appear in rows owned by q != rank
+    std::vector<std::pair<int, int>> need;
+#pragma omp parallel num_threads(options().threads)
+    {
+        std::vector<std::pair<int, int>> mine;
+#pragma omp for schedule(static) nowait
+        for (int g = 0; g < nrow_g; g++) {
+            const int q = rs.owner[g];
+            if (q == rank) continue;
+            for (int j = rp[g]; j < rp[g + 1]; j++)
+                if (cs.owner[ci[j]] == rank) mine.emplace_back(q, ci[j]);
+        }
+        std::sort(mine.begin(), mine.end());
+        mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+#pragma omp critical
+        need.insert(need.end(), mine.begin(), mine.end());
+    }
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+    for (size_t h = 0; h < need.size();) {
+        size_t e = h;
+        while (e < need.size() && need[e].first == need[h].first) e++;
+        op.send_rank.push_back(need[h].first);
+        op.send_ptr.push_back((int)h);
+        h = e;
+    }
+    op.send_ptr.push_back((int)need.size());
+    op.send_idx.resize(need.size());
+    for (size_t h = 0; h < need.size(); h++) op.send_idx[h] = cs.loc[need[h].second];
+    (void)nranks;
+}
+
+void transpose_csr(int nrow, int ncol, const int *rp, const int *ci, const double *v, std::vector<int> &trp,
+                   std::vector<int> &tci, std::vector<double> &tv) {
+    const int nnz = rp[nrow];
+    trp.assign((size_t)ncol + 1, 0);
+    tci.resize((size_t)std::max(nnz, 1));
+    tv.resize((size_t)std::max(nnz, 1));
+    for (int j = 0; j < nnz; j++) trp[ci[j] + 1]++;
+    for (int c = 0; c < ncol; c++) trp[c + 1] += trp[c];
+    std::vector<int> cur(trp.begin(), trp.end() - 1);
+    for (int i = 0; i < nrow; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int d = cur[ci[j]]++;
+            tci[d] = i;
+            tv[d] = v[j];
+        }
+}
+
+}  // namespace
+
+extern "C" {
+
+// tail_threshold: levels with at most this many rows are replicated (at least the coarsest always is, and level 0
+// is always distributed)
+void *sparsh_host_dist_plan(void *Sv, int nranks, int rank, int tail_threshold) {
+    AMG_solver *S = (AMG_solver *)Sv;
+    DistPlan *pl = new DistPlan();
+    pl->nranks = nranks;
+    pl->rank = rank;
+    pl->S = S;
+    pl->nlevels = S->l + 1;
+    if (S->l == 0) {
+        delete pl;
+        return nullptr;  // a single-level hierarchy has nothing to distribute
+    }
+    int nd = 1;
+    while (nd < S->l && S->Av[nd]->nrow > tail_threshold) nd++;
+    pl->nd = nd;
+    // index-space distributions of levels 0..nd
+    std::vector<Space> sp((size_t)nd + 1);
+    {
+        const int n0 = S->Av[0]->nrow;
+        sp[0].owner.resize(n0);
+        for (int r = 0; r < nranks; r++) {
+            const long b = (long)n0 * r / nranks, e = (long)n0 * (r + 1) / nranks;
+            std::fill(sp[0].owner.begin() + b, sp[0].owner.begin() + e, r);
+        }
+        finish_space(sp[0], nranks);
+    }
+    for (int l = 0; l < nd; l++) {
+        const sp_matrix_mg *P = S->Pv[l];
+        std::vector<int> &own = sp[l + 1].owner;
+        own.assign((size_t)P->ncol, -1);
+        for (int i = 0; i < P->nrow; i++)  // ascending i: the first fine row of every coarse row decides
+            for (int j = P->rowptr[i]; j < P->rowptr[i + 1]; j++)
+                if (own[P->colindex[j]] < 0) own[P->colindex[j]] = sp[l].owner[i];
+        for (int &o : own)
+            if (o < 0) o = 0;  // a coarse row nobody interpolates from (cannot happen with HEM/Beck)
+        finish_space(sp[l + 1], nranks);
+    }
+    pl->lev.resize(nd);
+    for (int l = 0; l < nd; l++) {
+        const sp_matrix_mg *A = S->Av[l], *P = S->Pv[l];
+        LevelLocal &L = pl->lev[l];
+        for (int g = 0; g < A->nrow; g++)
+            if (sp[l].owner[g] == rank) L.rows.push_back(g);
+        build_op(A->nrow, A->rowptr, A->colindex, A->val, A->diagonal, sp[l], sp[l], nranks, rank, L.A);
+        build_op(P->nrow, P->rowptr, P->colindex, P->val, nullptr, sp[l], sp[l + 1], nranks, rank, L.P);
+        std::vector<int> trp, tci;
+        std::vector<double> tv;
+        transpose_csr(P->nrow, P->ncol, P->rowptr, P->colindex, P->val, trp, tci, tv);
+        build_op(P->ncol, trp.data(), tci.data(), tv.data(), nullptr, sp[l + 1], sp[l], nranks, rank, L.R);
+    }
+    pl->tail_counts = sp[nd].count;
+    pl->tail_rows.clear();
+    for (int r = 0; r < nranks; r++)
+        for (int g = 0; g < (int)sp[nd].owner.size(); g++)
+            if (sp[nd].owner[g] == r) pl->tail_rows.push_back(g);
+    return pl;
+}
+
+void sparsh_host_dist_plan_free(void *plv) {
+    DistPlan *pl = (DistPlan *)plv;
+    if (!pl) return;
+    if (pl->device) sparsh_dist_hierarchy_destroy(pl->device);
+    delete pl;
+}
+
+int sparsh_host_dist_plan_levels(void *plv, int *nd, int *nlevels) {
+    DistPlan *pl = (DistPlan *)plv;
+    *nd = pl->nd;
+    *nlevels = pl->nlevels;
+    return 0;
+}
+
+// owned global row ids of distributed level l (l == nd: the first replicated level)
+int sparsh_host_dist_plan_rows(void *plv, int l, const int **rows) {
+    DistPlan *pl = (DistPlan *)plv;
+    if (l < pl->nd) {
+        *rows = pl->lev[l].rows.data();
+        return (int)pl->lev[l].rows.size();
+    }
+    int displ = 0;
+    for (int r = 0; r < pl->rank; r++) displ += pl->tail_counts[r];
+    *rows = pl->tail_rows.data() + displ;
+    return pl->tail_counts[pl->rank];
+}
+
+// which: 0 = A, 1 = P, 2 = R of distributed level l (arrays stay owned by the plan)
+int sparsh_host_dist_plan_op(void *plv, int l, int which, sparsh_dist_op_desc *out, const int **halo_global) {
+    DistPlan *pl = (DistPlan *)plv;
+    const OpLocal &op = which == 0 ? pl->lev[l].A : which == 1 ? pl->lev[l].P : pl->lev[l].R;
+    *out = op.desc();
+    if (halo_global) *halo_global = op.halo_global.data();
+    return 0;
+}
+
+// upload: distributed levels + replicated tail -> sparsh_dist_t (sparsh_dist_init must have been called)
+void *sparsh_host_dist_upload(void *plv) {
+    DistPlan *pl = (DistPlan *)plv;
+    if (pl->device) return pl->device;
+    const sparsh::Options &o = options();
+    std::vector<sparsh_dist_level_desc> d((size_t)pl->nd);
+    for (int l = 0; l < pl->nd; l++) {
+        d[l].A = pl->lev[l].A.desc();
+        d[l].P = pl->lev[l].P.desc();
+        d[l].R = pl->lev[l].R.desc();
+    }
+    AMG_solver *S = pl->S;
+    const int ntail = pl->nlevels - pl->nd;
+    std::vector<sparsh_level_desc> t((size_t)ntail);
+    for (int k = 0; k < ntail; k++) {
+        const int l = pl->nd + k;
+        std::memset(&t[k], 0, sizeof(sparsh_level_desc));
+        sp_matrix_mg *A = S->Av[l];
+        t[k].nrow = A->nrow;
+        t[k].nnz = A->rowptr[A->nrow];
+        t[k].rowptr = A->rowptr;
+        t[k].colindex = A->colindex;
+        t[k].val = A->val;
+        t[k].diag = A->diagonal;
+        if (l < S->l) {
+            sp_matrix_mg *P = S->Pv[l];
+            t[k].p_ncol = P->ncol;
+            t[k].p_nnz = P->rowptr[P->nrow];
+            t[k].p_rowptr = P->rowptr;
+            t[k].p_colindex = P->colindex;
+            t[k].p_val = P->val;
+        }
+    }
+    sparsh_params prm;
+    sparsh_params_default(&prm);
+    prm.omega = o.relax;
+    prm.use_graph = o.use_graph;
+    prm.pre_sweeps = prm.post_sweeps = o.sweeps;
+    int rc = sparsh_dist_hierarchy_create(pl->nd, d.data(), ntail, t.data(), pl->tail_counts.data(), pl->tail_rows.data(),
+                                          &prm, &pl->device);
+    if (rc != SPARSH_OK) {
+        std::fprintf(stderr, "sparsh_amg: distributed upload failed (%d): %s\n", rc, sparsh_last_error());
+        return nullptr;
+    }
+    return pl->device;
+}
+
+}  // extern "C"

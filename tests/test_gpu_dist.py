@@ -1,0 +1,30 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): N-GPU results against the 1-GPU path."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ngpus():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world,grid,threshold,graph", [(2, 64, 20000, 1), (2, 48, 3000, 0), (4, 64, 20000, 1)])
+def test_ngpu_matches_1gpu(world, grid, threshold, graph):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29800 + world + grid % 50),
+           os.path.join(HERE, "dist_gpu_worker.py"), str(grid), str(threshold), str(graph)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "DIST_GPU_OK" in out.stdout
