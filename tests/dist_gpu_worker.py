@@ -62,8 +62,9 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"DIST_GPU_OK world={world} grid={grid} nd={plan.nd}/{plan.nlevels} iterations={it} (1-GPU {it1})")
-    sp.capi.load().sparsh_dist_finalize()
-    dist.destroy_process_group()
+    from sparsh_amg_b200.distributed import shutdown
+
+    shutdown(dist, plan)
 
 
 if __name__ == "__main__":
