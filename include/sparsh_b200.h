@@ -138,6 +138,9 @@ typedef struct {
     int smoother;     /* 0: weighted Jacobi (AMG_solve_jacobi, src/AMG_phases.cpp:151-230)
                          1: multicolour SOR  (AMG_solve_SOR,   src/AMG_phases.cpp:234-306); pre/post_sweeps then count
                             SOR sweeps (the reference hard-codes 6, src/AMG_phases.cpp:251,265) */
+    int halo_mode;    /* multi-GPU only.  1 (default): boundary entries are stored straight into the neighbour's halo
+                         segment over NVLink peer memory by the packing kernel, with flag handshakes in device memory
+                         (no NCCL call on the exchange path); 0: grouped ncclSend/ncclRecv */
 } sparsh_params;
 void sparsh_params_default(sparsh_params *p);
 

@@ -31,7 +31,7 @@ class LevelDesc(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("omega", C.c_double), ("pre_sweeps", C.c_int), ("post_sweeps", C.c_int), ("use_graph", C.c_int),
-                ("coarse_mode", C.c_int), ("smoother", C.c_int)]
+                ("coarse_mode", C.c_int), ("smoother", C.c_int), ("halo_mode", C.c_int)]
 
 
 # every symbol include/sparsh_b200.h declares: (restype, argtypes)

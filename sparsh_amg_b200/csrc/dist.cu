@@ -1,17 +1,24 @@
-// dist.cu — multi-GPU solve phase: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+// dist.cu — multi-GPU solve phase: one process per GPU, NVLink 5 / NVSwitch.
 //
 // The reference has no distributed path (no MPI/NCCL anywhere).  This file row-partitions the same V-cycle / PCG:
 //   * operators: each rank owns a row block of A_l, P_l and R_l = P_l^T with columns relabelled to [owned | halo]
 //     positions (built on the host by host/dist_plan.cpp); the per-row entry order is preserved, so every row sum is
 //     bit-identical to the single-GPU one and only the reductions (dot products) see a different summation tree;
-//   * halo exchange: pack kernel -> grouped ncclSend/ncclRecv straight into the halo tail of the input vector, issued
-//     on a communication stream; interior rows (no halo reference) run meanwhile on the compute stream, boundary rows
-//     after the receive (north_star: "halo exchange ... overlapped with interior-row SpMV");
+//   * halo exchange, halo_mode 1 (default): every vector that can receive halo data lives in one cudaMalloc'ed ARENA per
+//     rank that all ranks map through CUDA IPC.  The packing kernel stores the boundary entries STRAIGHT INTO THE
+//     NEIGHBOUR'S HALO SEGMENT over NVLink (peer stores), fences, and raises a sequence flag in the neighbour's memory;
+//     the consumer runs its interior rows meanwhile, then a one-warp kernel waits on the flags (acquire, system scope)
+//     before the boundary rows run, and an ack flag travelling the other way protects the segment against being
+//     overwritten early.  Sequence counters live in device memory, so the whole exchange replays inside a CUDA graph and
+//     no NCCL call, host round trip or extra copy sits on the exchange path (~28 us per ncclSend/ncclRecv group ->
+//     a few us);
+//   * halo_mode 0: pack kernel -> grouped ncclSend/ncclRecv into the halo tail on a communication stream (fallback);
 //   * Krylov scalars: local fixed-tree partial -> ncclAllReduce(sum) of 1-2 doubles, in place in device memory;
 //   * small levels: gathered once per cycle with ncclAllGather and solved redundantly on every GPU by the single-GPU
 //     hierarchy code (levels whose halo would exceed their interior are latency-bound on a partitioned layout).
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <utility>
@@ -22,6 +29,9 @@
 using namespace sparsh;
 
 namespace {
+
+constexpr int MAX_NBR = 8;
+typedef unsigned long long u64;
 
 struct Comm {
     ncclComm_t comm = nullptr;
@@ -46,23 +56,105 @@ int nccl_fail(ncclResult_t r, const char *what, int line) {
 
 struct DistOp {
     sparsh_matrix_s *M = nullptr;
-    int nrow = 0, ncol_local = 0, nhalo = 0;
+    int id = 0;  // flag slot
+    int nrow = 0, ncol_local = 0, nhalo = 0, shift = 0;  // halo segment starts at ncol_local + shift
     std::vector<int> send_rank, send_ptr, recv_rank, recv_ptr;
+    std::vector<long long> peer_dst_off;  // per send neighbour: element offset of my slice inside ITS input vector
     int *d_send_idx = nullptr;
-    double *d_sendbuf = nullptr;
+    double *d_sendbuf = nullptr;  // NCCL mode only
     int ib = 0, ie = 0;
     bool needs_exchange() const { return !send_rank.empty() || !recv_rank.empty(); }
 };
 
 struct DistLevel {
     DistOp A, P, R;
-    int n = 0;        // owned rows of this level
-    int n_next = 0;   // owned rows of the next level
-    double *xbuf = nullptr, *tbuf = nullptr;  // [owned | halo(max of A, P_{l-1})]
+    int n = 0;       // owned rows of this level
+    int n_next = 0;  // owned rows of the next level
+    double *xbuf = nullptr, *tbuf = nullptr;  // [owned | halo(A_l) | halo(P_{l-1})]
     double *bbuf = nullptr;                   // owned (levels >= 1)
-    double *rbuf = nullptr;                   // [owned | halo(R)]
+    double *rbuf = nullptr;                   // [owned | halo(R_l)]
     size_t xcap = 0;
 };
+
+// ---- device-side signalling ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= want; gives up after ~2 s and raises *err so a broken handshake can never hang the GPU
+__device__ __forceinline__ void spin_until(const u64 *p, u64 want, int *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(err, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+struct PushArgs {
+    int nnbr;
+    int ptr[MAX_NBR + 1];          // prefix offsets into the send list
+    double *dst[MAX_NBR];          // peer address of my slice in the neighbour's halo segment
+    u64 *flag_dst[MAX_NBR];        // neighbour's "data from <me> for op" flag
+    const u64 *ack_local[MAX_NBR]; // my "neighbour has consumed my previous slice" flag
+};
+
+// producer: wait until the neighbours have consumed the previous slice, store the boundary entries into their halo
+// segments over NVLink, fence, raise the flags (last block to finish)
+__global__ void __launch_bounds__(256)
+    push_kernel(const double *__restrict__ x, const int *__restrict__ send_idx, int total, PushArgs a, u64 *seq,
+                unsigned int *ticket, int *err) {
+    __shared__ u64 s_prev;
+    if (threadIdx.x == 0) s_prev = *reinterpret_cast<volatile u64 *>(seq);
+    __syncthreads();
+    const u64 prev = s_prev;
+    if (threadIdx.x < a.nnbr) spin_until(a.ack_local[threadIdx.x], prev, err);
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < total) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < MAX_NBR; k++)
+            if (k < a.nnbr && i >= a.ptr[k]) q = k;
+        a.dst[q][i - a.ptr[q]] = x[send_idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            for (int q = 0; q < a.nnbr; q++) st_release_sys(a.flag_dst[q], prev + 1);
+            *reinterpret_cast<volatile u64 *>(seq) = prev + 1;
+            *ticket = 0u;
+            __threadfence();
+        }
+    }
+}
+
+struct WaitArgs {
+    int nnbr;
+    const u64 *flag_local[MAX_NBR];  // "data from neighbour q has landed" flags in my memory
+    u64 *ack_dst[MAX_NBR];           // neighbour q's ack slot for me
+};
+// consumer, before the boundary rows: one warp waits for every neighbour's slice
+__global__ void wait_kernel(WaitArgs a, u64 *expect, int *err) {
+    const u64 want = *reinterpret_cast<volatile u64 *>(expect) + 1;
+    if ((int)threadIdx.x < a.nnbr) spin_until(a.flag_local[threadIdx.x], want, err);
+    __syncwarp();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile u64 *>(expect) = want;
+}
+// consumer, after the boundary rows: tell the producers their slices may be overwritten
+__global__ void ack_kernel(WaitArgs a, const u64 *expect) {
+    const u64 v = *reinterpret_cast<const volatile u64 *>(expect);
+    if ((int)threadIdx.x < a.nnbr) st_release_sys(a.ack_dst[threadIdx.x], v);
+}
 
 __global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ x, const int *__restrict__ idx, int n, double *out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -84,31 +176,55 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restri
 }  // namespace
 
 struct sparsh_dist_s {
-    std::vector<DistLevel> lev;      // distributed levels 0..nd-1
+    std::vector<DistLevel> lev;          // distributed levels 0..nd-1
     sparsh_hierarchy_s *tail = nullptr;  // replicated levels nd..L
     sparsh_params prm;
-    int n_tail0 = 0;                 // global rows of the first replicated level
-    int tail_maxc = 0;               // padded per-rank count for the all-gather
-    int n_own_tail0 = 0;             // rows of that level owned by this rank
+    int n_tail0 = 0;      // global rows of the first replicated level
+    int tail_maxc = 0;    // padded per-rank count for the all-gather
+    int n_own_tail0 = 0;  // rows of that level owned by this rank
     double *tail_send = nullptr, *tail_recv = nullptr, *tail_b = nullptr, *tail_x = nullptr;
     int *d_tail_map = nullptr, *d_tail_rows = nullptr;
-    double *xtail_local = nullptr;   // owned part of X at level nd, [owned | halo(P_{nd-1})]
+    double *xtail_local = nullptr;  // owned part of X at level nd, [owned | halo(P_{nd-1})]
     double *btail_local = nullptr;
     // Krylov
     double *kv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_sc = nullptr, *h_sc = nullptr;
     std::vector<GraphEntry> graphs;
+    // arena shared through CUDA IPC: [flags | vectors]
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    bool peer = false;
+    int nops = 0;
+    std::vector<char *> peer_base;                    // [rank] mapped base of its arena (own base for me)
+    std::vector<std::pair<double *, size_t>> bufs;    // my halo-capable vectors: (pointer, byte offset in the arena)
+    std::vector<std::vector<long long>> peer_buf_off; // [rank][buffer id] byte offset in that rank's arena
+    u64 *seq = nullptr, *expect = nullptr;            // device counters per op (push / wait side)
+    unsigned int *ticket = nullptr;
+    int *d_err = nullptr, *h_err = nullptr;
 };
 
 namespace {
 
-int make_op(const sparsh_dist_op_desc &d, DistOp &op) {
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int make_op(const sparsh_dist_op_desc &d, int shift, int id, DistOp &op) {
+    op.id = id;
     op.nrow = d.nrow;
     op.ncol_local = d.ncol_local;
     op.nhalo = d.nhalo;
+    op.shift = shift;
     op.ib = d.interior_begin;
     op.ie = d.interior_end;
-    SP_TRY(sparsh_matrix_create(d.nrow, d.ncol_local + d.nhalo, d.nnz, d.rowptr, d.colindex, d.val, d.diag, &op.M));
+    // halo columns move behind the halo segment of the operator that shares this vector space (see DistLevel)
+    std::vector<int> ci;
+    const int *cols = d.colindex;
+    if (shift > 0) {
+        ci.assign(d.colindex, d.colindex + d.nnz);
+        for (int &c : ci)
+            if (c >= d.ncol_local) c += shift;
+        cols = ci.data();
+    }
+    SP_TRY(sparsh_matrix_create(d.nrow, d.ncol_local + shift + d.nhalo, d.nnz, d.rowptr, cols, d.val, d.diag, &op.M));
     op.send_rank.assign(d.send_rank, d.send_rank + d.n_send);
     op.send_ptr.assign(d.send_ptr, d.send_ptr + d.n_send + 1);
     op.recv_rank.assign(d.recv_rank, d.recv_rank + d.n_recv);
@@ -127,10 +243,68 @@ void free_op(DistOp &op) {
     cudaFree(op.d_sendbuf);
 }
 
-// Fill the halo tail of x = [owned | halo] for operator `op`.  Issued on the communication stream after everything
-// queued so far on the compute stream; the caller decides when the compute stream waits for it (finish_exchange).
-int start_exchange(const DistOp &op, double *x) {
-    if (!op.needs_exchange()) return SPARSH_OK;
+u64 *flag_slot(char *base, int nranks, int op, int kind, int r) {
+    return reinterpret_cast<u64 *>(base) + ((size_t)(op * 2 + kind) * nranks + r);
+}
+
+int buffer_id(const sparsh_dist_s *h, const double *x) {
+    for (size_t i = 0; i < h->bufs.size(); i++)
+        if (h->bufs[i].first == x) return (int)i;
+    return -1;
+}
+
+// ---- halo_mode 1: NVLink peer pushes --------------------------------------------------------------------------------
+int peer_push(sparsh_dist_s *h, const DistOp &op, double *x) {
+    if (op.send_rank.empty()) return SPARSH_OK;
+    Context &c = ctx();
+    Comm &m = comm();
+    const int bid = buffer_id(h, x);
+    SP_REQUIRE(bid >= 0, "halo exchange on a vector that is not in the shared arena");
+    PushArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.nnbr = (int)op.send_rank.size();
+    for (int s = 0; s < a.nnbr; s++) {
+        const int q = op.send_rank[s];
+        a.ptr[s] = op.send_ptr[s];
+        a.dst[s] = reinterpret_cast<double *>(h->peer_base[q] + h->peer_buf_off[q][bid]) + op.peer_dst_off[s];
+        a.flag_dst[s] = flag_slot(h->peer_base[q], m.nranks, op.id, 0, m.rank);
+        a.ack_local[s] = flag_slot(h->arena, m.nranks, op.id, 1, q);
+    }
+    a.ptr[a.nnbr] = op.send_ptr[a.nnbr];
+    const int total = op.send_ptr.back();
+    push_kernel<<<(total + 255) / 256, 256, 0, c.stream>>>(x, op.d_send_idx, total, a, h->seq + op.id, h->ticket + op.id, h->d_err);
+    count_launch();
+    return SPARSH_OK;
+}
+void wait_args(sparsh_dist_s *h, const DistOp &op, WaitArgs &a) {
+    Comm &m = comm();
+    std::memset(&a, 0, sizeof a);
+    a.nnbr = (int)op.recv_rank.size();
+    for (int r = 0; r < a.nnbr; r++) {
+        const int q = op.recv_rank[r];
+        a.flag_local[r] = flag_slot(h->arena, m.nranks, op.id, 0, q);
+        a.ack_dst[r] = flag_slot(h->peer_base[q], m.nranks, op.id, 1, m.rank);
+    }
+}
+int peer_wait(sparsh_dist_s *h, const DistOp &op) {
+    if (op.recv_rank.empty()) return SPARSH_OK;
+    WaitArgs a;
+    wait_args(h, op, a);
+    wait_kernel<<<1, 32, 0, ctx().stream>>>(a, h->expect + op.id, h->d_err);
+    count_launch();
+    return SPARSH_OK;
+}
+int peer_ack(sparsh_dist_s *h, const DistOp &op) {
+    if (op.recv_rank.empty()) return SPARSH_OK;
+    WaitArgs a;
+    wait_args(h, op, a);
+    ack_kernel<<<1, 32, 0, ctx().stream>>>(a, h->expect + op.id);
+    count_launch();
+    return SPARSH_OK;
+}
+
+// ---- halo_mode 0: NCCL point-to-point on a communication stream -----------------------------------------------------
+int nccl_start(const DistOp &op, double *x) {
     Context &c = ctx();
     Comm &m = comm();
     const int total = op.send_rank.empty() ? 0 : op.send_ptr.back();
@@ -145,32 +319,39 @@ int start_exchange(const DistOp &op, double *x) {
         SP_NCCL(ncclSend(op.d_sendbuf + op.send_ptr[s], (size_t)(op.send_ptr[s + 1] - op.send_ptr[s]), ncclDouble,
                          op.send_rank[s], m.comm, m.comm_stream));
     for (size_t r = 0; r < op.recv_rank.size(); r++)
-        SP_NCCL(ncclRecv(x + op.ncol_local + op.recv_ptr[r], (size_t)(op.recv_ptr[r + 1] - op.recv_ptr[r]), ncclDouble,
-                         op.recv_rank[r], m.comm, m.comm_stream));
+        SP_NCCL(ncclRecv(x + op.ncol_local + op.shift + op.recv_ptr[r], (size_t)(op.recv_ptr[r + 1] - op.recv_ptr[r]),
+                         ncclDouble, op.recv_rank[r], m.comm, m.comm_stream));
     SP_NCCL(ncclGroupEnd());
     SP_CUDA(cudaEventRecord(m.ev_done, m.comm_stream));
     return SPARSH_OK;
 }
-int finish_exchange(const DistOp &op) {
-    if (!op.needs_exchange()) return SPARSH_OK;
+int nccl_finish() {
     SP_CUDA(cudaStreamWaitEvent(ctx().stream, comm().ev_done, 0));
     return SPARSH_OK;
 }
 
-// y = epi(op x): halo exchange overlapped with the interior rows
-int apply(const DistOp &op, int epi, double *x, double *y, const EpiArgs &args) {
+// y = epi(op x): the halo travels while the interior rows are computed
+int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, const EpiArgs &args) {
+    if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
-    if (!op.needs_exchange() || reduces || op.ie <= op.ib) {
-        // (the fused reductions need one grid over all rows: exchange first, then a single launch)
-        SP_TRY(start_exchange(op, x));
-        SP_TRY(finish_exchange(op));
-        return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
+    // (the fused reductions need one grid over all rows, and tiny interiors are not worth a separate launch)
+    const bool split = !reduces && op.ie - op.ib >= 4096;
+    if (h->peer)
+        SP_TRY(peer_push(h, op, x));
+    else
+        SP_TRY(nccl_start(op, x));
+    if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
+    if (h->peer)
+        SP_TRY(peer_wait(h, op));
+    else
+        SP_TRY(nccl_finish());
+    if (split) {
+        if (op.ib > 0) SP_TRY(launch_csr(op.M, epi, x, y, args, 0, op.ib));
+        if (op.ie < op.nrow) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ie, op.nrow));
+    } else {
+        SP_TRY(launch_csr(op.M, epi, x, y, args, 0, op.nrow));
     }
-    SP_TRY(start_exchange(op, x));
-    SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));  // interior rows while the halo is in flight
-    SP_TRY(finish_exchange(op));
-    if (op.ib > 0) SP_TRY(launch_csr(op.M, epi, x, y, args, 0, op.ib));
-    if (op.ie < op.nrow) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ie, op.nrow));
+    if (h->peer) SP_TRY(peer_ack(h, op));
     return SPARSH_OK;
 }
 
@@ -195,14 +376,14 @@ int dist_smooth(sparsh_dist_s *h, DistLevel &L, const double *b, double *&cur, d
             a.xi = cur;
             a.d = L.A.M->diag;
             a.omega = h->prm.omega;
-            SP_TRY(apply(L.A, EPI_JACOBI, cur, other, a));
+            SP_TRY(apply(h, L.A, EPI_JACOBI, cur, other, a));
         }
         std::swap(cur, other);
     }
     return SPARSH_OK;
 }
 
-// x must have halo capacity (lev[0].xcap doubles).  One V-cycle, enqueue only.
+// x must be a halo-capable arena vector of level 0.  One V-cycle, enqueue only.
 int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_zero) {
     Context &c = ctx();
     Comm &m = comm();
@@ -221,9 +402,9 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
         SP_TRY(dist_smooth(h, L, B[l], X[l], T[l], h->prm.pre_sweeps, l > 0 || x_is_zero));
         EpiArgs a;
         a.b = B[l];
-        SP_TRY(apply(L.A, EPI_RESID, X[l], L.rbuf, a));
+        SP_TRY(apply(h, L.A, EPI_RESID, X[l], L.rbuf, a));
         double *bnext = l + 1 < nd ? h->lev[l + 1].bbuf : h->btail_local;
-        SP_TRY(apply(L.R, EPI_SPMV, L.rbuf, bnext, EpiArgs()));
+        SP_TRY(apply(h, L.R, EPI_SPMV, L.rbuf, bnext, EpiArgs()));
     }
     // replicated tail: all-gather the restricted right-hand side, solve redundantly, keep the owned rows
     if (m.nranks > 1) {
@@ -244,7 +425,7 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
     }
     for (int l = nd; l > 0; l--) {
         DistLevel &F = h->lev[l - 1];
-        SP_TRY(apply(F.P, EPI_PROLONG, X[l], X[l - 1], EpiArgs()));
+        SP_TRY(apply(h, F.P, EPI_PROLONG, X[l], X[l - 1], EpiArgs()));
         SP_TRY(dist_smooth(h, F, B[l - 1], X[l - 1], T[l - 1], h->prm.post_sweeps, false));
     }
     if (X[0] != x) SP_CUDA(cudaMemcpyAsync(x, X[0], sizeof(double) * (size_t)h->lev[0].n, cudaMemcpyDeviceToDevice, c.stream));
@@ -254,8 +435,7 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
 
 template <class F>
 int dist_run_graphed(sparsh_dist_s *h, const void *k0, const void *k1, int tag, F body) {
-    // NCCL point-to-point and collective calls are capturable; the communication stream joins the capture through
-    // the ready/done events
+    // peer-push exchanges are plain kernels; NCCL collectives (and point-to-point calls in halo_mode 0) are capturable
     Context &c = ctx();
     if (!h->prm.use_graph) return body();
     GraphEntry *ent = nullptr;
@@ -288,6 +468,37 @@ int dist_run_graphed(sparsh_dist_s *h, const void *k0, const void *k1, int tag, 
     }
     SP_CUDA(cudaGraphLaunch(ent->exec, c.stream));
     c.launches += ent->kernels;
+    return SPARSH_OK;
+}
+
+int check_handshake(sparsh_dist_s *h) {
+    if (!h->peer) return SPARSH_OK;
+    SP_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    SP_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (*h->h_err) {
+        set_error("multi-GPU halo handshake timed out (a neighbour never signalled)");
+        return SPARSH_ERR_CUDA;
+    }
+    return SPARSH_OK;
+}
+
+// all ranks exchange equally sized byte blocks (setup only)
+int allgather_bytes(const void *mine, size_t bytes, std::vector<char> &all) {
+    Comm &m = comm();
+    all.assign(bytes * (size_t)m.nranks, 0);
+    if (m.nranks == 1) {
+        std::memcpy(all.data(), mine, bytes);
+        return SPARSH_OK;
+    }
+    char *d_in = nullptr, *d_out = nullptr;
+    SP_CUDA(cudaMalloc(&d_in, bytes));
+    SP_CUDA(cudaMalloc(&d_out, bytes * (size_t)m.nranks));
+    SP_CUDA(cudaMemcpy(d_in, mine, bytes, cudaMemcpyHostToDevice));
+    SP_NCCL(ncclAllGather(d_in, d_out, bytes, ncclChar, m.comm, ctx().stream));
+    SP_CUDA(cudaStreamSynchronize(ctx().stream));
+    SP_CUDA(cudaMemcpy(all.data(), d_out, all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
     return SPARSH_OK;
 }
 
@@ -357,25 +568,143 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     else
         sparsh_params_default(&h->prm);
     SP_REQUIRE(h->prm.smoother == 0, "the distributed path implements the Jacobi smoother only");
+    h->peer = h->prm.halo_mode == 1 && m.nranks > 1 && m.nranks <= MAX_NBR;
+    h->nops = 3 * nd;
     h->lev.resize(nd);
+
+    // ---- operators.  Vector space of level l is read by A_l (halo segment right after the owned entries) and by
+    //      P_{l-1} (its halo segment sits behind A_l's, so the two exchanges never share memory)
     for (int l = 0; l < nd; l++) {
         DistLevel &L = h->lev[l];
-        SP_TRY(make_op(lev[l].A, L.A));
-        SP_TRY(make_op(lev[l].P, L.P));
-        SP_TRY(make_op(lev[l].R, L.R));
+        SP_TRY(make_op(lev[l].A, 0, 3 * l + 0, L.A));
+        SP_TRY(make_op(lev[l].P, l + 1 < nd ? lev[l + 1].A.nhalo : 0, 3 * l + 1, L.P));
+        SP_TRY(make_op(lev[l].R, 0, 3 * l + 2, L.R));
         L.n = lev[l].A.nrow;
         L.n_next = lev[l].R.nrow;
-        int halo = lev[l].A.nhalo;
-        if (l > 0) halo = std::max(halo, lev[l - 1].P.nhalo);
-        L.xcap = (size_t)L.n + (size_t)halo + 2;
-        SP_CUDA(cudaMalloc(&L.tbuf, sizeof(double) * L.xcap));
-        SP_CUDA(cudaMalloc(&L.rbuf, sizeof(double) * ((size_t)L.n + lev[l].R.nhalo + 2)));
-        if (l > 0) {
-            SP_CUDA(cudaMalloc(&L.xbuf, sizeof(double) * L.xcap));
-            SP_CUDA(cudaMalloc(&L.bbuf, sizeof(double) * ((size_t)L.n + 2)));
+        L.xcap = (size_t)L.n + lev[l].A.nhalo + (l > 0 ? lev[l - 1].P.nhalo : 0) + 2;
+    }
+    h->n_own_tail0 = tail_counts[m.rank];
+    SP_REQUIRE(h->n_own_tail0 == h->lev[nd - 1].n_next, "owned rows of the first replicated level disagree with R");
+
+    // ---- arena: flags first, then every vector that can be the target of a halo exchange (same ORDER on all ranks)
+    const size_t flag_bytes = align_up(sizeof(u64) * 2 * (size_t)h->nops * m.nranks, 256);
+    std::vector<size_t> want;  // bytes per buffer, in buffer-id order
+    for (int l = 0; l < nd; l++) {
+        want.push_back(sizeof(double) * h->lev[l].xcap);                               // tbuf
+        want.push_back(sizeof(double) * ((size_t)h->lev[l].n + lev[l].R.nhalo + 2));   // rbuf
+        if (l > 0) want.push_back(sizeof(double) * h->lev[l].xcap);                    // xbuf
+    }
+    want.push_back(sizeof(double) * ((size_t)h->n_own_tail0 + lev[nd - 1].P.nhalo + 2));  // xtail_local
+    for (int i = 0; i < 5; i++) want.push_back(sizeof(double) * h->lev[0].xcap);          // Krylov vectors
+    size_t total = flag_bytes;
+    std::vector<size_t> off(want.size());
+    for (size_t i = 0; i < want.size(); i++) {
+        off[i] = total;
+        total += align_up(want[i], 256);
+    }
+    h->arena_bytes = total;
+    SP_CUDA(cudaMalloc(&h->arena, total));
+    SP_CUDA(cudaMemset(h->arena, 0, total));
+    size_t k = 0;
+    auto take = [&]() {
+        double *p = reinterpret_cast<double *>(h->arena + off[k]);
+        h->bufs.emplace_back(p, off[k]);
+        k++;
+        return p;
+    };
+    for (int l = 0; l < nd; l++) {
+        h->lev[l].tbuf = take();
+        h->lev[l].rbuf = take();
+        if (l > 0) h->lev[l].xbuf = take();
+    }
+    h->xtail_local = take();
+    for (int i = 0; i < 5; i++) h->kv[i] = take();
+    for (int l = 1; l < nd; l++) SP_CUDA(cudaMalloc(&h->lev[l].bbuf, sizeof(double) * ((size_t)h->lev[l].n + 2)));
+
+    SP_CUDA(cudaMalloc(&h->seq, sizeof(u64) * (size_t)h->nops));
+    SP_CUDA(cudaMalloc(&h->expect, sizeof(u64) * (size_t)h->nops));
+    SP_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)h->nops));
+    SP_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
+    SP_CUDA(cudaMallocHost(&h->h_err, sizeof(int)));
+    SP_CUDA(cudaMemset(h->seq, 0, sizeof(u64) * (size_t)h->nops));
+    SP_CUDA(cudaMemset(h->expect, 0, sizeof(u64) * (size_t)h->nops));
+    SP_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int) * (size_t)h->nops));
+    SP_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    *h->h_err = 0;
+
+    // ---- peer mapping + the two small tables every producer needs about its consumers
+    h->peer_base.assign(m.nranks, nullptr);
+    h->peer_base[m.rank] = h->arena;
+    if (h->peer) {
+        cudaIpcMemHandle_t mine;
+        SP_CUDA(cudaIpcGetMemHandle(&mine, h->arena));
+        std::vector<char> all;
+        SP_TRY(allgather_bytes(&mine, sizeof mine, all));
+        bool ok = true;
+        for (int r = 0; r < m.nranks && ok; r++) {
+            if (r == m.rank) continue;
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, all.data() + (size_t)r * sizeof hd, sizeof hd);
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+            }
+            h->peer_base[r] = (char *)p;
+        }
+        // every rank must take the same decision
+        int okv = ok ? 1 : 0;
+        std::vector<char> oks;
+        SP_TRY(allgather_bytes(&okv, sizeof okv, oks));
+        for (int r = 0; r < m.nranks; r++) {
+            int v;
+            std::memcpy(&v, oks.data() + (size_t)r * sizeof v, sizeof v);
+            if (!v) h->peer = false;
         }
     }
-    // replicated tail
+    {
+        // buffer offsets of every rank
+        std::vector<long long> mine(h->bufs.size());
+        for (size_t i = 0; i < h->bufs.size(); i++) mine[i] = (long long)h->bufs[i].second;
+        std::vector<char> all;
+        SP_TRY(allgather_bytes(mine.data(), sizeof(long long) * mine.size(), all));
+        h->peer_buf_off.assign(m.nranks, std::vector<long long>(mine.size()));
+        for (int r = 0; r < m.nranks; r++)
+            std::memcpy(h->peer_buf_off[r].data(), all.data() + (size_t)r * sizeof(long long) * mine.size(),
+                        sizeof(long long) * mine.size());
+        // where each sender's slice lands inside MY input vectors: table[op][sender] = element offset, -1 = none
+        std::vector<long long> land((size_t)h->nops * m.nranks, -1);
+        auto fill = [&](const DistOp &op) {
+            for (size_t r = 0; r < op.recv_rank.size(); r++)
+                land[(size_t)op.id * m.nranks + op.recv_rank[r]] = (long long)op.ncol_local + op.shift + op.recv_ptr[r];
+        };
+        for (auto &L : h->lev) {
+            fill(L.A);
+            fill(L.P);
+            fill(L.R);
+        }
+        SP_TRY(allgather_bytes(land.data(), sizeof(long long) * land.size(), all));
+        auto resolve = [&](DistOp &op) -> int {
+            op.peer_dst_off.resize(op.send_rank.size());
+            for (size_t s = 0; s < op.send_rank.size(); s++) {
+                const int q = op.send_rank[s];
+                long long v;
+                std::memcpy(&v, all.data() + ((size_t)q * land.size() + (size_t)op.id * m.nranks + m.rank) * sizeof(long long),
+                            sizeof v);
+                SP_REQUIRE(v >= 0, "exchange plans of two ranks disagree");
+                op.peer_dst_off[s] = v;
+            }
+            SP_REQUIRE((int)op.send_rank.size() <= MAX_NBR && (int)op.recv_rank.size() <= MAX_NBR, "too many neighbours");
+            return SPARSH_OK;
+        };
+        for (auto &L : h->lev) {
+            SP_TRY(resolve(L.A));
+            SP_TRY(resolve(L.P));
+            SP_TRY(resolve(L.R));
+        }
+    }
+
+    // ---- replicated tail
     sparsh_params tp = h->prm;
     tp.use_graph = 0;  // its launches are captured as part of the enclosing distributed graph
     SP_TRY(sparsh_hierarchy_create(ntail, tail, &tp, &h->tail));
@@ -388,12 +717,10 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     }
     SP_REQUIRE(displ == h->n_tail0, "tail_counts do not add up to the rows of the first replicated level");
     h->tail_maxc = std::max(maxc, 1);
-    h->n_own_tail0 = tail_counts[m.rank];
-    SP_REQUIRE(h->n_own_tail0 == h->lev[nd - 1].n_next, "owned rows of the first replicated level disagree with R");
     std::vector<int> map((size_t)h->tail_maxc * m.nranks, -1);
     displ = 0;
     for (int r = 0; r < m.nranks; r++) {
-        for (int k = 0; k < tail_counts[r]; k++) map[(size_t)r * h->tail_maxc + k] = tail_rows[displ + k];
+        for (int q = 0; q < tail_counts[r]; q++) map[(size_t)r * h->tail_maxc + q] = tail_rows[displ + q];
         displ += tail_counts[r];
     }
     if (m.nranks == 1) map.assign(tail_rows, tail_rows + h->n_tail0);
@@ -406,16 +733,21 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     SP_CUDA(cudaMalloc(&h->tail_recv, sizeof(double) * (size_t)h->tail_maxc * m.nranks));
     SP_CUDA(cudaMalloc(&h->tail_b, sizeof(double) * ((size_t)h->n_tail0 + 2)));
     SP_CUDA(cudaMalloc(&h->tail_x, sizeof(double) * ((size_t)h->n_tail0 + 2)));
-    SP_CUDA(cudaMalloc(&h->xtail_local, sizeof(double) * ((size_t)h->n_own_tail0 + lev[nd - 1].P.nhalo + 2)));
     SP_CUDA(cudaMalloc(&h->btail_local, sizeof(double) * ((size_t)h->n_own_tail0 + 2)));
     SP_CUDA(cudaMalloc(&h->d_sc, sizeof(double) * 16));
     SP_CUDA(cudaMallocHost(&h->h_sc, sizeof(double) * 16));
+    SP_CUDA(cudaDeviceSynchronize());
+    if (m.nranks > 1) {  // nobody may push before every arena is mapped and zeroed
+        SP_NCCL(ncclAllReduce(h->d_sc, h->d_sc, 1, ncclDouble, ncclSum, m.comm, ctx().stream));
+        SP_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
     *out = h;
     return SPARSH_OK;
 }
 
 int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     if (!h) return SPARSH_OK;
+    Comm &m = comm();
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     for (auto &g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -423,21 +755,24 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
         free_op(L.A);
         free_op(L.P);
         free_op(L.R);
-        cudaFree(L.xbuf);
-        cudaFree(L.tbuf);
         cudaFree(L.bbuf);
-        cudaFree(L.rbuf);
     }
     sparsh_hierarchy_destroy(h->tail);
+    for (int r = 0; r < (int)h->peer_base.size(); r++)
+        if (r != m.rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaFree(h->arena);
     cudaFree(h->tail_send);
     cudaFree(h->tail_recv);
     cudaFree(h->tail_b);
     cudaFree(h->tail_x);
     cudaFree(h->d_tail_map);
     cudaFree(h->d_tail_rows);
-    cudaFree(h->xtail_local);
     cudaFree(h->btail_local);
-    for (int i = 0; i < 6; i++) cudaFree(h->kv[i]);
+    cudaFree(h->seq);
+    cudaFree(h->expect);
+    cudaFree(h->ticket);
+    cudaFree(h->d_err);
+    cudaFreeHost(h->h_err);
     cudaFree(h->d_sc);
     cudaFreeHost(h->h_sc);
     delete h;
@@ -454,18 +789,18 @@ int sparsh_dist_spmv(sparsh_dist_t h, int level, const double *d_x_local, double
     SP_REQUIRE(h != nullptr && level >= 0 && level < (int)h->lev.size(), "bad level");
     DistLevel &L = h->lev[level];
     SP_CUDA(cudaMemcpyAsync(L.tbuf, d_x_local, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, ctx().stream));
-    return apply(L.A, EPI_SPMV, L.tbuf, d_y_local, EpiArgs());
+    SP_TRY(apply(h, L.A, EPI_SPMV, L.tbuf, d_y_local, EpiArgs()));
+    return check_handshake(h);
 }
 
 int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_local, int cycles, int x_is_zero) {
     SP_REQUIRE(h != nullptr && cycles >= 0, "bad arguments");
     DistLevel &L0 = h->lev[0];
-    if (!h->kv[1]) SP_CUDA(cudaMalloc(&h->kv[1], sizeof(double) * L0.xcap));
     double *z = h->kv[1];  // halo-capable staging for the caller's x
     SP_CUDA(cudaMemcpyAsync(z, d_x_local, sizeof(double) * (size_t)L0.n, cudaMemcpyDeviceToDevice, ctx().stream));
     for (int k = 0; k < cycles; k++) SP_TRY(enqueue_dist_vcycle(h, d_b_local, z, x_is_zero && k == 0));
     SP_CUDA(cudaMemcpyAsync(d_x_local, z, sizeof(double) * (size_t)L0.n, cudaMemcpyDeviceToDevice, ctx().stream));
-    return SPARSH_OK;
+    return check_handshake(h);
 }
 
 // Same arithmetic as cg_impl(precond = true) in krylov.cu (reference src/AMG_main_solvers.cpp:107-167); the three
@@ -475,19 +810,18 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
     Context &c = ctx();
     DistLevel &L0 = h->lev[0];
     const size_t n = (size_t)L0.n;
-    for (int i = 0; i < 5; i++)
-        if (!h->kv[i]) SP_CUDA(cudaMalloc(&h->kv[i], sizeof(double) * L0.xcap));
     double *r = h->kv[0], *z = h->kv[1], *p = h->kv[2], *Ap = h->kv[3], *xs = h->kv[4];
     double *sc = h->d_sc;
     enum { S_PAP = 0, S_RZ = 1, S_RZNEW = 2, S_RR = 3 };
     auto read_rr = [&]() -> int {
         SP_CUDA(cudaMemcpyAsync(h->h_sc + S_RR, sc + S_RR, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (h->peer) SP_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         return SPARSH_OK;
     };
     SP_CUDA(cudaMemcpyAsync(xs, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
     EpiArgs a;
     a.b = b;
-    SP_TRY(apply(L0.A, EPI_RESID, xs, r, a));
+    SP_TRY(apply(h, L0.A, EPI_RESID, xs, r, a));
     SP_TRY(k_dot(n, r, r, sc + S_RR));
     SP_TRY(allreduce_sum(sc + S_RR, 1));
     SP_TRY(dist_run_graphed(h, r, z, 1, [&]() { return enqueue_dist_vcycle(h, r, z, true); }));
@@ -500,12 +834,11 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
     if (hist) hist[0] = r1;
 
     auto body = [&]() -> int {
-        // Ap = A p and the local part of p.Ap: the fused reduction needs the full row range, so the exchange is not
-        // overlapped here (one of ~16 operator applications per level-0 visit)
+        // Ap = A p and the local part of p.Ap (the fused reduction runs over the full row range: no interior split)
         EpiArgs e;
         e.xi = p;
         e.red_out = sc + S_PAP;
-        SP_TRY(apply(L0.A, EPI_SPMV_DOT, p, Ap, e));
+        SP_TRY(apply(h, L0.A, EPI_SPMV_DOT, p, Ap, e));
         SP_TRY(allreduce_sum(sc + S_PAP, 1));
         SP_TRY(k_pcg_update_xr(n, p, Ap, xs, r, sc + S_RZ, sc + S_PAP, sc + S_RR));
         SP_TRY(allreduce_sum(sc + S_RR, 1));
@@ -517,11 +850,16 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
         SP_TRY(read_rr());
         return SPARSH_OK;
     };
-    int count = 0;
+    int count = 0, rc = SPARSH_OK;
     while (count < max_iter && r1 > tol) {
         count++;
         SP_TRY(dist_run_graphed(h, x, b, 10, body));
         SP_CUDA(cudaStreamSynchronize(c.stream));
+        if (h->peer && *h->h_err) {
+            set_error("multi-GPU halo handshake timed out (a neighbour never signalled)");
+            rc = SPARSH_ERR_CUDA;
+            break;
+        }
         r1 = std::sqrt(h->h_sc[S_RR]);
         if (hist) hist[count] = r1;
         if (!std::isfinite(r1)) break;
@@ -529,6 +867,7 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
     SP_CUDA(cudaMemcpyAsync(x, xs, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
     SP_CUDA(cudaStreamSynchronize(c.stream));
     if (iters_out) *iters_out = count;
+    if (rc != SPARSH_OK) return rc;
     return r1 <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
 }
 

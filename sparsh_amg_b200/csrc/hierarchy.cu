@@ -102,6 +102,7 @@ void sparsh_params_default(sparsh_params *p) {
     p->use_graph = 1;
     p->coarse_mode = 0;
     p->smoother = 0;
+    p->halo_mode = 1;
 }
 
 int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const sparsh_params *params,

@@ -143,7 +143,8 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
 
     grid = args.grid
     threads = max(1, (os.cpu_count() or 1) // world)
-    host.set_options(threads=threads, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=1)
+    host.set_options(threads=threads, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=1,
+                     halo_mode=args.halo_mode)
     t0 = time.time()
     A = host.HostMatrix.poisson3d(grid, grid, grid)
     amg = host.HostAmg(A)  # every rank builds the (sequential) host hierarchy, then keeps only its part on the GPU
@@ -246,7 +247,8 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
                            "true_rel_residual": r_true / float(np.sqrt(n)),
                            "ms_per_pcg_iteration": solve_s * 1e3 / max(it, 1), "timing": "CUDA events, max over ranks",
                            "l2": "inputs larger than L2 per rank at the finest levels", "cuda_graph": True,
-                           "host_setup_seconds": t_setup, "tail_threshold_rows": args.tail_threshold},
+                           "host_setup_seconds": t_setup, "tail_threshold_rows": args.tail_threshold,
+                           "halo_exchange": "NVLink peer-memory push + flags" if args.halo_mode == 1 else "ncclSend/ncclRecv"},
                 "e2e": {"value": float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8,
                         "d2h_bytes_per_step": n * 8},
                 "gpu_launches": int(launches) * world,

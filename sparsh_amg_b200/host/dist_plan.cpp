@@ -335,6 +335,7 @@ void *sparsh_host_dist_upload(void *plv) {
     prm.omega = o.relax;
     prm.use_graph = o.use_graph;
     prm.pre_sweeps = prm.post_sweeps = o.sweeps;
+    prm.halo_mode = o.halo_mode;
     int rc = sparsh_dist_hierarchy_create(pl->nd, d.data(), ntail, t.data(), pl->tail_counts.data(), pl->tail_rows.data(),
                                           &prm, &pl->device);
     if (rc != SPARSH_OK) {

@@ -83,6 +83,7 @@ struct Options {
     int coarsening = COARSEN_HEM;  // the shipped default (reference src/AMG_phases.cpp:61; Beck is :63)
     int max_iter = 10000;          // iteration cap (the reference's AMG and BiCGStab loops have none)
     int use_graph = 1;             // CUDA-graph the V-cycle / Krylov iteration
+    int halo_mode = 1;             // multi-GPU halo exchange: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv
 };
 Options &options();
 

@@ -20,12 +20,14 @@ def main():
     grid = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     threshold = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     use_graph = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    halo_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist.init_process_group(backend="nccl", device_id=device)
     sp.init(local_rank)
     init_comm(dist, rank, world, device)
-    host.set_options(threads=4, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=use_graph)
+    host.set_options(threads=4, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=use_graph,
+                     halo_mode=halo_mode)
     A = host.HostMatrix.poisson3d(grid, grid, grid)
     amg = host.HostAmg(A)
     n = A.nrow
@@ -61,7 +63,8 @@ def main():
     assert it2 == it and np.array_equal(hist2, hist)
     dist.barrier()
     if rank == 0:
-        print(f"DIST_GPU_OK world={world} grid={grid} nd={plan.nd}/{plan.nlevels} iterations={it} (1-GPU {it1})")
+        print(f"DIST_GPU_OK world={world} grid={grid} nd={plan.nd}/{plan.nlevels} iterations={it} (1-GPU {it1}) "
+              f"halo_mode={halo_mode} graph={use_graph}")
     from sparsh_amg_b200.distributed import shutdown
 
     shutdown(dist, plan)
