@@ -143,19 +143,6 @@ struct WaitArgs {
     const u64 *flag_local[MAX_NBR];  // "data from neighbour q has landed" flags in my memory
     u64 *ack_dst[MAX_NBR];           // neighbour q's ack slot for me
 };
-// consumer, before the boundary rows: one warp waits for every neighbour's slice
-__global__ void wait_kernel(WaitArgs a, u64 *expect, int *err) {
-    const u64 want = *reinterpret_cast<volatile u64 *>(expect) + 1;
-    if ((int)threadIdx.x < a.nnbr) spin_until(a.flag_local[threadIdx.x], want, err);
-    __syncwarp();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile u64 *>(expect) = want;
-}
-// consumer, after the boundary rows: tell the producers their slices may be overwritten
-__global__ void ack_kernel(WaitArgs a, const u64 *expect) {
-    const u64 v = *reinterpret_cast<const volatile u64 *>(expect);
-    if ((int)threadIdx.x < a.nnbr) st_release_sys(a.ack_dst[threadIdx.x], v);
-}
-
 __global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ x, const int *__restrict__ idx, int n, double *out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < n) out[i] = x[idx[i]];
@@ -199,7 +186,7 @@ struct sparsh_dist_s {
     std::vector<std::pair<double *, size_t>> bufs;    // my halo-capable vectors: (pointer, byte offset in the arena)
     std::vector<std::vector<long long>> peer_buf_off; // [rank][buffer id] byte offset in that rank's arena
     u64 *seq = nullptr, *expect = nullptr;            // device counters per op (push / wait side)
-    unsigned int *ticket = nullptr;
+    unsigned int *ticket = nullptr, *ticket2 = nullptr;  // last-block tickets: producers / consumers
     int *d_err = nullptr, *h_err = nullptr;
 };
 
@@ -286,21 +273,18 @@ void wait_args(sparsh_dist_s *h, const DistOp &op, WaitArgs &a) {
         a.ack_dst[r] = flag_slot(h->peer_base[q], m.nranks, op.id, 1, m.rank);
     }
 }
-int peer_wait(sparsh_dist_s *h, const DistOp &op) {
-    if (op.recv_rank.empty()) return SPARSH_OK;
+// consumer side, fused into the CSR kernel that reads the halo: wait for the flags at CTA start, ack from the last CTA
+void halo_sync(sparsh_dist_s *h, const DistOp &op, HaloSync &hs) {
     WaitArgs a;
     wait_args(h, op, a);
-    wait_kernel<<<1, 32, 0, ctx().stream>>>(a, h->expect + op.id, h->d_err);
-    count_launch();
-    return SPARSH_OK;
-}
-int peer_ack(sparsh_dist_s *h, const DistOp &op) {
-    if (op.recv_rank.empty()) return SPARSH_OK;
-    WaitArgs a;
-    wait_args(h, op, a);
-    ack_kernel<<<1, 32, 0, ctx().stream>>>(a, h->expect + op.id);
-    count_launch();
-    return SPARSH_OK;
+    hs.nnbr = a.nnbr;
+    for (int r = 0; r < a.nnbr; r++) {
+        hs.flag_local[r] = a.flag_local[r];
+        hs.ack_dst[r] = a.ack_dst[r];
+    }
+    hs.expect = h->expect + op.id;
+    hs.ticket = h->ticket2 + op.id;
+    hs.err = h->d_err;
 }
 
 // ---- halo_mode 0: NCCL point-to-point on a communication stream -----------------------------------------------------
@@ -335,24 +319,20 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, con
     if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
     // (the fused reductions need one grid over all rows, and tiny interiors are not worth a separate launch)
-    const bool split = !reduces && op.ie - op.ib >= 4096;
-    if (h->peer)
+    const bool split = !reduces && op.ie - op.ib >= 4096 && (op.ib > 0 || op.ie < op.nrow);
+    HaloSync hs;
+    if (h->peer) {
         SP_TRY(peer_push(h, op, x));
-    else
-        SP_TRY(nccl_start(op, x));
-    if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
-    if (h->peer)
-        SP_TRY(peer_wait(h, op));
-    else
-        SP_TRY(nccl_finish());
-    if (split) {
-        if (op.ib > 0) SP_TRY(launch_csr(op.M, epi, x, y, args, 0, op.ib));
-        if (op.ie < op.nrow) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ie, op.nrow));
+        halo_sync(h, op, hs);
     } else {
-        SP_TRY(launch_csr(op.M, epi, x, y, args, 0, op.nrow));
+        SP_TRY(nccl_start(op, x));
     }
-    if (h->peer) SP_TRY(peer_ack(h, op));
-    return SPARSH_OK;
+    if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));  // interior rows: no halo entry referenced
+    if (!h->peer) SP_TRY(nccl_finish());
+    // the rows that read the halo, in one launch (both boundary strips, or everything when there is no split)
+    if (split)
+        return launch_csr2(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, &hs);
+    return launch_csr2(op.M, epi, x, y, args, 0, op.nrow, 0, 0, &hs);
 }
 
 int allreduce_sum(double *d_vals, int count) {
@@ -624,6 +604,8 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     SP_CUDA(cudaMalloc(&h->seq, sizeof(u64) * (size_t)h->nops));
     SP_CUDA(cudaMalloc(&h->expect, sizeof(u64) * (size_t)h->nops));
     SP_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)h->nops));
+    SP_CUDA(cudaMalloc(&h->ticket2, sizeof(unsigned int) * (size_t)h->nops));
+    SP_CUDA(cudaMemset(h->ticket2, 0, sizeof(unsigned int) * (size_t)h->nops));
     SP_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
     SP_CUDA(cudaMallocHost(&h->h_err, sizeof(int)));
     SP_CUDA(cudaMemset(h->seq, 0, sizeof(u64) * (size_t)h->nops));
@@ -771,6 +753,7 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     cudaFree(h->seq);
     cudaFree(h->expect);
     cudaFree(h->ticket);
+    cudaFree(h->ticket2);
     cudaFree(h->d_err);
     cudaFreeHost(h->h_err);
     cudaFree(h->d_sc);

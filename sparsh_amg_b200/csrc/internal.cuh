@@ -112,6 +112,24 @@ struct EpiArgs {
 };
 int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
                int row_end);
+// rows [b1,e1) followed by rows [b2,e2) in ONE launch (the two boundary strips of a row block)
+struct RowRange {
+    int b1, e1, b2, e2, nblk1;
+};
+// multi-GPU: flag handshake fused into the consuming kernel (dist.cu).  Every CTA waits (acquire, system scope) until
+// each neighbour's halo slice has landed before it gathers x; the last CTA to finish advances the sequence counter and
+// stores the acks that allow the neighbours to overwrite the slices.
+typedef unsigned long long sparsh_u64;
+struct HaloSync {
+    int nnbr = 0;
+    const sparsh_u64 *flag_local[8];
+    sparsh_u64 *ack_dst[8];
+    sparsh_u64 *expect = nullptr;
+    unsigned int *ticket = nullptr;
+    int *err = nullptr;
+};
+int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
+                int b2, int e2, const HaloSync *hs);
 
 // ---- BLAS-1 (blas1.cu) -------------------------------------------------------------------------------------
 int k_fill(double *x, size_t n, double v);

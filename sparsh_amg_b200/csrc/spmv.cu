@@ -57,6 +57,60 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Multi-GPU flag handshake fused into the consumer (see HaloSync in internal.cuh, producer side in dist.cu)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ sparsh_u64 ld_acquire_sys_u64(const sparsh_u64 *p) {
+    sparsh_u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(sparsh_u64 *p, sparsh_u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// called by every thread of the CTA, before the first gather of x; contains a CTA barrier
+__device__ __forceinline__ sparsh_u64 halo_wait(const HaloSync &hs) {
+    if (hs.nnbr == 0) return 0;
+    const sparsh_u64 want = *reinterpret_cast<const volatile sparsh_u64 *>(hs.expect) + 1;
+    if ((int)threadIdx.x < hs.nnbr) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(hs.flag_local[threadIdx.x]) < want) {
+            if (clock64() - t0 > 4000000000ll) {  // ~2 s: report instead of hanging the GPU
+                atomicExch(hs.err, 1);
+                break;
+            }
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    return want;
+}
+// called by every thread of the CTA after its last read of x
+__device__ __forceinline__ void halo_done(const HaloSync &hs, sparsh_u64 want) {
+    if (hs.nnbr == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(hs.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *reinterpret_cast<volatile sparsh_u64 *>(hs.expect) = want;
+            for (int q = 0; q < hs.nnbr; q++) st_release_sys_u64(hs.ack_dst[q], want);
+            *hs.ticket = 0u;
+            __threadfence();
+        }
+    }
+}
+__device__ __forceinline__ void block_rows(const RowRange &rr, int rows_per_cta, int &first, int &end) {
+    int blk = blockIdx.x;
+    first = rr.b1;
+    end = rr.e1;
+    if (blk >= rr.nblk1) {
+        blk -= rr.nblk1;
+        first = rr.b2;
+        end = rr.e2;
+    }
+    first += blk * rows_per_cta;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Epilogues.  Arithmetic and evaluation order follow the reference's CPU path:
 //   store_residual   r = b - (A x)                              src/AMG_cycle_utilities.cpp:120-121
 //   jacobi           x += (omega*(b - A x))/d                   src/AMG_smoothers.cpp:62-71
@@ -162,8 +216,8 @@ __global__ void __launch_bounds__(1024) finalize_partials_kernel(const double *_
 // ---------------------------------------------------------------------------------------------------------
 template <int THREADS, int EPI>
 __global__ void __launch_bounds__(THREADS)
-    csr_stream_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end, int cap,
-                      double *partials, unsigned int *ticket) {
+    csr_stream_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, int cap, double *partials,
+                      HaloSync hs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sval = reinterpret_cast<double *>(smem_raw);
     int *scol = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(double));
@@ -171,7 +225,8 @@ __global__ void __launch_bounds__(THREADS)
     __shared__ int s_a0;
 
     const int tid = threadIdx.x;
-    const int r0 = row_begin + blockIdx.x * THREADS;
+    int r0, row_end;
+    block_rows(rr, THREADS, r0, row_end);
     const int nrows = min(THREADS, row_end - r0);
 
     if (tid == 0) {
@@ -200,6 +255,7 @@ __global__ void __launch_bounds__(THREADS)
         hi = A.rowptr[row + 1];
         e = epi_load<EPI>(args, y, row);
     }
+    const sparsh_u64 hs_want = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed (no-op otherwise)
     __syncthreads();  // barrier init and s_a0 visible to everyone
     mbar_wait(&bar, 0);
 
@@ -223,6 +279,7 @@ __global__ void __launch_bounds__(THREADS)
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
+    halo_done(hs, hs_want);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -230,9 +287,11 @@ __global__ void __launch_bounds__(THREADS)
 // ---------------------------------------------------------------------------------------------------------
 template <int THREADS, int EPI>
 __global__ void __launch_bounds__(THREADS)
-    csr_scalar_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end,
-                      double *partials, unsigned int *ticket) {
-    const int row = row_begin + blockIdx.x * THREADS + threadIdx.x;
+    csr_scalar_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
+    int r0, row_end;
+    block_rows(rr, THREADS, r0, row_end);
+    const int row = r0 + threadIdx.x;
+    const sparsh_u64 hs_want = halo_wait(hs);
     double contrib = 0.0;
     if (row < row_end) {
         const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
@@ -243,6 +302,7 @@ __global__ void __launch_bounds__(THREADS)
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
+    halo_done(hs, hs_want);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -250,12 +310,14 @@ __global__ void __launch_bounds__(THREADS)
 // ---------------------------------------------------------------------------------------------------------
 template <int LANES, int EPI>
 __global__ void __launch_bounds__(256)
-    csr_vector_kernel(CsrView A, const double *x, double *y, EpiArgs args, int row_begin, int row_end,
-                      double *partials, unsigned int *ticket) {
+    csr_vector_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
     constexpr int ROWS_PER_CTA = 256 / LANES;
     const int lane = threadIdx.x % LANES;
-    const int row = row_begin + blockIdx.x * ROWS_PER_CTA + threadIdx.x / LANES;
+    int r0, row_end;
+    block_rows(rr, ROWS_PER_CTA, r0, row_end);
+    const int row = r0 + threadIdx.x / LANES;
     const bool active = row < row_end;
+    const sparsh_u64 hs_want = halo_wait(hs);
     double s = 0.0;
     EpiRegs e;
     if (active) {
@@ -269,13 +331,39 @@ __global__ void __launch_bounds__(256)
     double contrib = 0.0;
     if (active && lane == 0) contrib = epi_store<EPI>(args, e, s, y, row);
     if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
+    halo_done(hs, hs_want);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
+struct LaunchDesc {
+    RowRange rr;
+    int rows1, rows2;
+    HaloSync hs;
+};
+
+static int grid_for(LaunchDesc &d, int rows_per_cta) {
+    const int n1 = (d.rows1 + rows_per_cta - 1) / rows_per_cta, n2 = (d.rows2 + rows_per_cta - 1) / rows_per_cta;
+    d.rr.nblk1 = n1;
+    return n1 + n2;
+}
+
+template <int EPI>
+static int finish_launch(int grid, const EpiArgs &args) {
+    Context &c = ctx();
+    count_launch();
+    SP_CUDA(cudaGetLastError());
+    if (EpiTraits<EPI>::reduces) {
+        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, grid, args.red_out);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+    }
+    return SPARSH_OK;
+}
+
 template <int THREADS, int EPI>
-static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
     static bool attr_set = false;
     if (!attr_set) {
@@ -286,111 +374,100 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     const int win = THREADS == 256 ? A->win256 : A->win128;
     const int cap = ((win + 8) + 3) & ~3;
     const size_t smem = (size_t)cap * 12;
-    const int grid = (re - rb + THREADS - 1) / THREADS;
+    const int grid = grid_for(d, THREADS);
     if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_stream_kernel<THREADS, EPI><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, rb, re, cap, c.partials,
-                                                                      c.ticket);
-    count_launch();
-    SP_CUDA(cudaGetLastError());
-    if (EpiTraits<EPI>::reduces) {
-        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
-        count_launch();
-        SP_CUDA(cudaGetLastError());
-    }
-    return SPARSH_OK;
+    csr_stream_kernel<THREADS, EPI><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
+    return finish_launch<EPI>(grid, args);
 }
 
 template <int EPI>
-static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
-    const int grid = (re - rb + 255) / 256;
+    const int grid = grid_for(d, 256);
     if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_scalar_kernel<256, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, rb, re, c.partials, c.ticket);
-    count_launch();
-    SP_CUDA(cudaGetLastError());
-    if (EpiTraits<EPI>::reduces) {
-        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
-        count_launch();
-        SP_CUDA(cudaGetLastError());
-    }
-    return SPARSH_OK;
+    csr_scalar_kernel<256, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    return finish_launch<EPI>(grid, args);
 }
 
 template <int LANES, int EPI>
-static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
+static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
-    constexpr int ROWS = 256 / LANES;
-    const long long grid = ((long long)(re - rb) + ROWS - 1) / ROWS;
+    const int grid = grid_for(d, 256 / LANES);
     if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_vector_kernel<LANES, EPI><<<(unsigned)grid, 256, 0, c.stream>>>(A->view(), x, y, args, rb, re, c.partials,
-                                                                        c.ticket);
-    count_launch();
-    SP_CUDA(cudaGetLastError());
-    if (EpiTraits<EPI>::reduces) {
-        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, (int)grid, args.red_out);
-        count_launch();
-        SP_CUDA(cudaGetLastError());
-    }
-    return SPARSH_OK;
+    csr_vector_kernel<LANES, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    return finish_launch<EPI>(grid, args);
 }
 
 template <int EPI>
-static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, int rb, int re) {
-    if (re <= rb) {
+static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
+    if (d.rows1 + d.rows2 <= 0) {
         if (EpiTraits<EPI>::reduces) SP_CUDA(cudaMemsetAsync(args.red_out, 0, sizeof(double), ctx().stream));
         return SPARSH_OK;
     }
     switch (A->kind) {
         case KIND_SCALAR:
-            return launch_scalar<EPI>(A, x, y, args, rb, re);
+            return launch_scalar<EPI>(A, x, y, args, d);
         case KIND_STREAM:
-            return A->threads == 128 ? launch_stream<128, EPI>(A, x, y, args, rb, re)
-                                     : launch_stream<256, EPI>(A, x, y, args, rb, re);
+            return A->threads == 128 ? launch_stream<128, EPI>(A, x, y, args, d) : launch_stream<256, EPI>(A, x, y, args, d);
         default:
             switch (A->lanes) {
                 case 2:
-                    return launch_vector<2, EPI>(A, x, y, args, rb, re);
+                    return launch_vector<2, EPI>(A, x, y, args, d);
                 case 4:
-                    return launch_vector<4, EPI>(A, x, y, args, rb, re);
+                    return launch_vector<4, EPI>(A, x, y, args, d);
                 case 8:
-                    return launch_vector<8, EPI>(A, x, y, args, rb, re);
+                    return launch_vector<8, EPI>(A, x, y, args, d);
                 case 16:
-                    return launch_vector<16, EPI>(A, x, y, args, rb, re);
+                    return launch_vector<16, EPI>(A, x, y, args, d);
                 default:
-                    return launch_vector<32, EPI>(A, x, y, args, rb, re);
+                    return launch_vector<32, EPI>(A, x, y, args, d);
             }
     }
 }
 
-int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
-               int row_end) {
+int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
+                int b2, int e2, const HaloSync *hs) {
+    LaunchDesc d;
+    d.rr = RowRange{b1, e1, b2, e2, 0};
+    d.rows1 = e1 > b1 ? e1 - b1 : 0;
+    d.rows2 = e2 > b2 ? e2 - b2 : 0;
+    if (hs) d.hs = *hs;
+    if (d.hs.nnbr > 0 && d.rows1 + d.rows2 <= 0) {
+        set_error("halo handshake attached to an empty launch");
+        return SPARSH_ERR_INVALID;
+    }
     switch (epi) {
         case EPI_SPMV:
-            return launch_epi<EPI_SPMV>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_SPMV>(A, x, y, args, d);
         case EPI_RESID:
-            return launch_epi<EPI_RESID>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_RESID>(A, x, y, args, d);
         case EPI_JACOBI:
-            return launch_epi<EPI_JACOBI>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_JACOBI>(A, x, y, args, d);
         case EPI_PROLONG:
-            return launch_epi<EPI_PROLONG>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_PROLONG>(A, x, y, args, d);
         case EPI_SOR:
-            return launch_epi<EPI_SOR>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_SOR>(A, x, y, args, d);
         case EPI_SPMV_DOT:
-            return launch_epi<EPI_SPMV_DOT>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_SPMV_DOT>(A, x, y, args, d);
         case EPI_RESNORM:
-            return launch_epi<EPI_RESNORM>(A, x, y, args, row_begin, row_end);
+            return launch_epi<EPI_RESNORM>(A, x, y, args, d);
     }
     set_error("unknown epilogue");
     return SPARSH_ERR_INVALID;
+}
+
+int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
+               int row_end) {
+    return launch_csr2(A, epi, x, y, args, row_begin, row_end, 0, 0, nullptr);
 }
 
 }  // namespace sparsh
