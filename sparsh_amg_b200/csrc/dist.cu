@@ -62,6 +62,7 @@ struct DistOp {
     std::vector<long long> peer_dst_off;  // per send neighbour: element offset of my slice inside ITS input vector
     int *d_send_idx = nullptr;
     double *d_sendbuf = nullptr;  // NCCL mode only
+    int *d_pm_ptr = nullptr, *d_pm_nbr = nullptr, *d_pm_off = nullptr;  // A ops: row -> (neighbour slot, position) it is sent to
     int ib = 0, ie = 0;
     bool needs_exchange() const { return !send_rank.empty() || !recv_rank.empty(); }
 };
@@ -187,6 +188,9 @@ struct sparsh_dist_s {
     std::vector<std::vector<long long>> peer_buf_off; // [rank][buffer id] byte offset in that rank's arena
     u64 *seq = nullptr, *expect = nullptr;            // device counters per op (push / wait side)
     unsigned int *ticket = nullptr, *ticket2 = nullptr;  // last-block tickets: producers / consumers
+    std::vector<int> buf_level;       // buffer id -> level whose A operator reads it (-1: none)
+    std::vector<int> halo_ready;      // buffer id -> (op id + 1) whose halo slices the producing kernel already pushed, 0 = none
+    double **d_pm_tab = nullptr;      // [buffer id][neighbour slot] peer address of my slice (fused Jacobi push)
     int *d_err = nullptr, *h_err = nullptr;
 };
 
@@ -224,10 +228,34 @@ int make_op(const sparsh_dist_op_desc &d, int shift, int id, DistOp &op) {
     }
     return SPARSH_OK;
 }
+// rows of a square operator that some neighbour needs, as a CSR over the local rows (for the fused Jacobi push)
+int make_push_map(const sparsh_dist_op_desc &d, DistOp &op) {
+    std::vector<int> ptr((size_t)d.nrow + 1, 0);
+    const int total = d.n_send ? d.send_ptr[d.n_send] : 0;
+    for (int k = 0; k < total; k++) ptr[d.send_idx[k] + 1]++;
+    for (int i = 0; i < d.nrow; i++) ptr[i + 1] += ptr[i];
+    std::vector<int> nbr((size_t)std::max(total, 1)), off((size_t)std::max(total, 1)), cur(ptr.begin(), ptr.end() - 1);
+    for (int s = 0; s < d.n_send; s++)
+        for (int k = d.send_ptr[s]; k < d.send_ptr[s + 1]; k++) {
+            const int pos = cur[d.send_idx[k]]++;
+            nbr[pos] = s;
+            off[pos] = k - d.send_ptr[s];
+        }
+    SP_CUDA(cudaMalloc(&op.d_pm_ptr, sizeof(int) * ptr.size()));
+    SP_CUDA(cudaMalloc(&op.d_pm_nbr, sizeof(int) * nbr.size()));
+    SP_CUDA(cudaMalloc(&op.d_pm_off, sizeof(int) * off.size()));
+    SP_CUDA(cudaMemcpy(op.d_pm_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+    SP_CUDA(cudaMemcpy(op.d_pm_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice));
+    SP_CUDA(cudaMemcpy(op.d_pm_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+    return SPARSH_OK;
+}
 void free_op(DistOp &op) {
     sparsh_matrix_destroy(op.M);
     cudaFree(op.d_send_idx);
     cudaFree(op.d_sendbuf);
+    cudaFree(op.d_pm_ptr);
+    cudaFree(op.d_pm_nbr);
+    cudaFree(op.d_pm_off);
 }
 
 u64 *flag_slot(char *base, int nranks, int op, int kind, int r) {
@@ -314,25 +342,77 @@ int nccl_finish() {
     return SPARSH_OK;
 }
 
-// y = epi(op x): the halo travels while the interior rows are computed
-int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, const EpiArgs &args) {
+// run `f` with the library's current stream temporarily replaced (launch_csr and friends enqueue on ctx().stream)
+struct StreamSwap {
+    cudaStream_t saved;
+    explicit StreamSwap(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
+    ~StreamSwap() { ctx().stream = saved; }
+};
+int fork_aux() {
+    Comm &m = comm();
+    SP_CUDA(cudaEventRecord(m.ev_ready, ctx().stream));
+    SP_CUDA(cudaStreamWaitEvent(m.comm_stream, m.ev_ready, 0));
+    return SPARSH_OK;
+}
+int join_aux() {
+    Comm &m = comm();
+    SP_CUDA(cudaEventRecord(m.ev_done, m.comm_stream));
+    SP_CUDA(cudaStreamWaitEvent(ctx().stream, m.ev_done, 0));
+    return SPARSH_OK;
+}
+
+// y = epi(op x).  The rows that touch the halo (and, for the fused Jacobi, the rows a neighbour needs) form the two
+// boundary strips; they run on the auxiliary stream — generic push if the halo of x is not already on its way, then ONE
+// kernel that waits for the flags, computes, optionally stores the new values into the neighbours and signals — while
+// the interior rows run concurrently on the main stream.  `push_output`: y is the next input of this same operator.
+int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, EpiArgs args, bool push_output = false) {
     if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
     // (the fused reductions need one grid over all rows, and tiny interiors are not worth a separate launch)
     const bool split = !reduces && op.ie - op.ib >= 4096 && (op.ib > 0 || op.ie < op.nrow);
-    HaloSync hs;
-    if (h->peer) {
-        SP_TRY(peer_push(h, op, x));
-        halo_sync(h, op, hs);
-    } else {
+    if (!h->peer) {
         SP_TRY(nccl_start(op, x));
+        if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
+        SP_TRY(nccl_finish());
+        if (split) return launch_csr2(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, nullptr);
+        return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     }
-    if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));  // interior rows: no halo entry referenced
-    if (!h->peer) SP_TRY(nccl_finish());
-    // the rows that read the halo, in one launch (both boundary strips, or everything when there is no split)
-    if (split)
-        return launch_csr2(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, &hs);
-    return launch_csr2(op.M, epi, x, y, args, 0, op.nrow, 0, 0, &hs);
+    Comm &m = comm();
+    const int bx = buffer_id(h, x);
+    SP_REQUIRE(bx >= 0, "halo exchange on a vector that is not in the shared arena");
+    const bool need_push = h->halo_ready[bx] != op.id + 1;
+    h->halo_ready[bx] = 0;
+    HaloSync hs;
+    halo_sync(h, op, hs);
+    EpiArgs bargs = args;  // boundary strips may carry the fused push
+    if (push_output && epi == EPI_JACOBI && !op.send_rank.empty()) {
+        const int by = buffer_id(h, y);
+        SP_REQUIRE(by >= 0 && h->buf_level[by] >= 0, "fused push into a vector outside the arena");
+        bargs.pm_ptr = op.d_pm_ptr;
+        bargs.pm_nbr = op.d_pm_nbr;
+        bargs.pm_off = op.d_pm_off;
+        bargs.pm_dst = h->d_pm_tab + (size_t)by * MAX_NBR;
+        hs.nsend = (int)op.send_rank.size();
+        for (int s = 0; s < hs.nsend; s++) {
+            const int q = op.send_rank[s];
+            hs.flag_dst[s] = flag_slot(h->peer_base[q], m.nranks, op.id, 0, m.rank);
+            hs.ack_local[s] = flag_slot(h->arena, m.nranks, op.id, 1, q);
+        }
+        hs.seq = h->seq + op.id;
+        h->halo_ready[by] = op.id + 1;
+    }
+    if (!split) {
+        if (need_push) SP_TRY(peer_push(h, op, x));
+        return launch_csr2(op.M, epi, x, y, bargs, 0, op.nrow, 0, 0, &hs);
+    }
+    SP_TRY(fork_aux());
+    {
+        StreamSwap sw(m.comm_stream);
+        if (need_push) SP_TRY(peer_push(h, op, x));
+        SP_TRY(launch_csr2(op.M, epi, x, y, bargs, 0, op.ib, op.ie, op.nrow, &hs));
+    }
+    SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));  // interior rows: no halo entry referenced, nothing to send
+    return join_aux();
 }
 
 int allreduce_sum(double *d_vals, int count) {
@@ -342,7 +422,9 @@ int allreduce_sum(double *d_vals, int count) {
     return SPARSH_OK;
 }
 
-int dist_smooth(sparsh_dist_s *h, DistLevel &L, const double *b, double *&cur, double *&other, int sweeps, bool zero) {
+// `feeds_A`: the vector this smoothing step leaves behind is next read by A_l itself (residual after pre-smoothing)
+int dist_smooth(sparsh_dist_s *h, DistLevel &L, const double *b, double *&cur, double *&other, int sweeps, bool zero,
+                bool feeds_A) {
     if (sweeps == 0) {
         if (zero) SP_TRY(k_fill(cur, (size_t)L.n, 0.0));
         return SPARSH_OK;
@@ -356,7 +438,7 @@ int dist_smooth(sparsh_dist_s *h, DistLevel &L, const double *b, double *&cur, d
             a.xi = cur;
             a.d = L.A.M->diag;
             a.omega = h->prm.omega;
-            SP_TRY(apply(h, L.A, EPI_JACOBI, cur, other, a));
+            SP_TRY(apply(h, L.A, EPI_JACOBI, cur, other, a, s + 1 < sweeps || feeds_A));
         }
         std::swap(cur, other);
     }
@@ -379,7 +461,7 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
     B[nd] = h->btail_local;
     for (int l = 0; l < nd; l++) {
         DistLevel &L = h->lev[l];
-        SP_TRY(dist_smooth(h, L, B[l], X[l], T[l], h->prm.pre_sweeps, l > 0 || x_is_zero));
+        SP_TRY(dist_smooth(h, L, B[l], X[l], T[l], h->prm.pre_sweeps, l > 0 || x_is_zero, true));
         EpiArgs a;
         a.b = B[l];
         SP_TRY(apply(h, L.A, EPI_RESID, X[l], L.rbuf, a));
@@ -406,7 +488,7 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
     for (int l = nd; l > 0; l--) {
         DistLevel &F = h->lev[l - 1];
         SP_TRY(apply(h, F.P, EPI_PROLONG, X[l], X[l - 1], EpiArgs()));
-        SP_TRY(dist_smooth(h, F, B[l - 1], X[l - 1], T[l - 1], h->prm.post_sweeps, false));
+        SP_TRY(dist_smooth(h, F, B[l - 1], X[l - 1], T[l - 1], h->prm.post_sweeps, false, false));
     }
     if (X[0] != x) SP_CUDA(cudaMemcpyAsync(x, X[0], sizeof(double) * (size_t)h->lev[0].n, cudaMemcpyDeviceToDevice, c.stream));
     SP_CUDA(cudaGetLastError());
@@ -557,6 +639,7 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     for (int l = 0; l < nd; l++) {
         DistLevel &L = h->lev[l];
         SP_TRY(make_op(lev[l].A, 0, 3 * l + 0, L.A));
+        SP_TRY(make_push_map(lev[l].A, L.A));
         SP_TRY(make_op(lev[l].P, l + 1 < nd ? lev[l + 1].A.nhalo : 0, 3 * l + 1, L.P));
         SP_TRY(make_op(lev[l].R, 0, 3 * l + 2, L.R));
         L.n = lev[l].A.nrow;
@@ -586,19 +669,21 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     SP_CUDA(cudaMalloc(&h->arena, total));
     SP_CUDA(cudaMemset(h->arena, 0, total));
     size_t k = 0;
-    auto take = [&]() {
+    auto take = [&](int level) {
         double *p = reinterpret_cast<double *>(h->arena + off[k]);
         h->bufs.emplace_back(p, off[k]);
+        h->buf_level.push_back(level);
         k++;
         return p;
     };
     for (int l = 0; l < nd; l++) {
-        h->lev[l].tbuf = take();
-        h->lev[l].rbuf = take();
-        if (l > 0) h->lev[l].xbuf = take();
+        h->lev[l].tbuf = take(l);
+        h->lev[l].rbuf = take(-1);
+        if (l > 0) h->lev[l].xbuf = take(l);
     }
-    h->xtail_local = take();
-    for (int i = 0; i < 5; i++) h->kv[i] = take();
+    h->xtail_local = take(-1);
+    for (int i = 0; i < 5; i++) h->kv[i] = take(0);
+    h->halo_ready.assign(h->bufs.size(), 0);
     for (int l = 1; l < nd; l++) SP_CUDA(cudaMalloc(&h->lev[l].bbuf, sizeof(double) * ((size_t)h->lev[l].n + 2)));
 
     SP_CUDA(cudaMalloc(&h->seq, sizeof(u64) * (size_t)h->nops));
@@ -684,6 +769,19 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
             SP_TRY(resolve(L.P));
             SP_TRY(resolve(L.R));
         }
+        // fused Jacobi push: where my slice of A_l's exchange lands when the OUTPUT vector is buffer `bid`
+        std::vector<double *> tab(h->bufs.size() * MAX_NBR, nullptr);
+        for (size_t bid = 0; bid < h->bufs.size(); bid++) {
+            if (h->buf_level[bid] < 0 || !h->peer) continue;
+            const DistOp &A = h->lev[h->buf_level[bid]].A;
+            for (size_t sidx = 0; sidx < A.send_rank.size(); sidx++) {
+                const int q = A.send_rank[sidx];
+                tab[bid * MAX_NBR + sidx] =
+                    reinterpret_cast<double *>(h->peer_base[q] + h->peer_buf_off[q][bid]) + A.peer_dst_off[sidx];
+            }
+        }
+        SP_CUDA(cudaMalloc(&h->d_pm_tab, sizeof(double *) * tab.size()));
+        SP_CUDA(cudaMemcpy(h->d_pm_tab, tab.data(), sizeof(double *) * tab.size(), cudaMemcpyHostToDevice));
     }
 
     // ---- replicated tail
@@ -754,6 +852,7 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     cudaFree(h->expect);
     cudaFree(h->ticket);
     cudaFree(h->ticket2);
+    cudaFree(h->d_pm_tab);
     cudaFree(h->d_err);
     cudaFreeHost(h->h_err);
     cudaFree(h->d_sc);

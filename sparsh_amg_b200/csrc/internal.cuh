@@ -109,6 +109,11 @@ struct EpiArgs {
     const double *d = nullptr;
     double omega = 0.0;
     double *red_out = nullptr;  // device scalar receiving the reduction (EPI_SPMV_DOT / EPI_RESNORM)
+    // multi-GPU, EPI_JACOBI only: rows whose new value a neighbour needs store it ALSO into that neighbour's halo
+    // segment over NVLink (compute fused with the halo exchange of the next sweep).  CSR over the local rows:
+    // entries pm_ptr[row]..pm_ptr[row+1] give (neighbour slot, position inside the slice sent to it).
+    const int *pm_ptr = nullptr, *pm_nbr = nullptr, *pm_off = nullptr;
+    double *const *pm_dst = nullptr;  // device table: per neighbour slot, the peer address of my slice (output vector)
 };
 int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
                int row_end);
@@ -121,10 +126,17 @@ struct RowRange {
 // stores the acks that allow the neighbours to overwrite the slices.
 typedef unsigned long long sparsh_u64;
 struct HaloSync {
+    // consumer side: this kernel reads halo slices
     int nnbr = 0;
     const sparsh_u64 *flag_local[8];
     sparsh_u64 *ack_dst[8];
     sparsh_u64 *expect = nullptr;
+    // producer side (fused Jacobi): this kernel also writes the NEXT slices into its neighbours (EpiArgs::pm_*); it
+    // first makes sure they have consumed the previous ones, and the last CTA raises their flags
+    int nsend = 0;
+    sparsh_u64 *flag_dst[8];
+    const sparsh_u64 *ack_local[8];
+    sparsh_u64 *seq = nullptr;
     unsigned int *ticket = nullptr;
     int *err = nullptr;
 };

@@ -67,32 +67,50 @@ __device__ __forceinline__ sparsh_u64 ld_acquire_sys_u64(const sparsh_u64 *p) {
 __device__ __forceinline__ void st_release_sys_u64(sparsh_u64 *p, sparsh_u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// called by every thread of the CTA, before the first gather of x; contains a CTA barrier
-__device__ __forceinline__ sparsh_u64 halo_wait(const HaloSync &hs) {
-    if (hs.nnbr == 0) return 0;
-    const sparsh_u64 want = *reinterpret_cast<const volatile sparsh_u64 *>(hs.expect) + 1;
-    if ((int)threadIdx.x < hs.nnbr) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys_u64(hs.flag_local[threadIdx.x]) < want) {
-            if (clock64() - t0 > 4000000000ll) {  // ~2 s: report instead of hanging the GPU
-                atomicExch(hs.err, 1);
-                break;
-            }
-            __nanosleep(32);
+struct HaloTurn {
+    sparsh_u64 want, prev;
+};
+__device__ __forceinline__ void spin_ge(const sparsh_u64 *p, sparsh_u64 v, int *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(p) < v) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: report instead of hanging the GPU
+            atomicExch(err, 1);
+            break;
         }
+        __nanosleep(32);
     }
-    __syncthreads();
-    return want;
 }
-// called by every thread of the CTA after its last read of x
-__device__ __forceinline__ void halo_done(const HaloSync &hs, sparsh_u64 want) {
-    if (hs.nnbr == 0) return;
+// called by every thread of the CTA, before the first gather of x; contains a CTA barrier
+__device__ __forceinline__ HaloTurn halo_wait(const HaloSync &hs) {
+    HaloTurn t;
+    t.want = 0;
+    t.prev = 0;
+    if (hs.nnbr == 0 && hs.nsend == 0) return t;
+    if (hs.nnbr > 0) t.want = *reinterpret_cast<const volatile sparsh_u64 *>(hs.expect) + 1;
+    if (hs.nsend > 0) t.prev = *reinterpret_cast<const volatile sparsh_u64 *>(hs.seq);
+    const int tid = threadIdx.x;
+    if (tid < hs.nnbr) spin_ge(hs.flag_local[tid], t.want, hs.err);                          // slices have landed
+    if (tid >= 8 && tid - 8 < hs.nsend) spin_ge(hs.ack_local[tid - 8], t.prev, hs.err);      // old slices consumed
+    __syncthreads();
+    return t;
+}
+// called by every thread of the CTA after its last read of x and its last remote store
+__device__ __forceinline__ void halo_done(const HaloSync &hs, const HaloTurn &t) {
+    if (hs.nnbr == 0 && hs.nsend == 0) return;
+    if (hs.nsend > 0) __threadfence_system();  // my remote stores are performed before anyone sees the flag
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(hs.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *reinterpret_cast<volatile sparsh_u64 *>(hs.expect) = want;
-            for (int q = 0; q < hs.nnbr; q++) st_release_sys_u64(hs.ack_dst[q], want);
+        const unsigned int k = atomicAdd(hs.ticket, 1u);
+        if (k == gridDim.x - 1) {
+            if (hs.nnbr > 0) {
+                *reinterpret_cast<volatile sparsh_u64 *>(hs.expect) = t.want;
+                for (int q = 0; q < hs.nnbr; q++) st_release_sys_u64(hs.ack_dst[q], t.want);
+            }
+            if (hs.nsend > 0) {
+                __threadfence_system();
+                for (int q = 0; q < hs.nsend; q++) st_release_sys_u64(hs.flag_dst[q], t.prev + 1);
+                *reinterpret_cast<volatile sparsh_u64 *>(hs.seq) = t.prev + 1;
+            }
             *hs.ticket = 0u;
             __threadfence();
         }
@@ -144,7 +162,11 @@ __device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, 
         y[row] = __dsub_rn(e.b, s);
     } else if (EPI == EPI_JACOBI) {
         double h = __dsub_rn(e.b, s);
-        y[row] = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
+        const double v = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
+        y[row] = v;
+        if (a.pm_ptr) {  // fused halo push: the neighbours' next sweep reads this entry
+            for (int k = a.pm_ptr[row]; k < a.pm_ptr[row + 1]; k++) a.pm_dst[a.pm_nbr[k]][a.pm_off[k]] = v;
+        }
     } else if (EPI == EPI_PROLONG) {
         y[row] = __dadd_rn(s, e.xi);
     } else if (EPI == EPI_SOR) {
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(THREADS)
         hi = A.rowptr[row + 1];
         e = epi_load<EPI>(args, y, row);
     }
-    const sparsh_u64 hs_want = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed (no-op otherwise)
+    const HaloTurn hs_turn = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed (no-op otherwise)
     __syncthreads();  // barrier init and s_a0 visible to everyone
     mbar_wait(&bar, 0);
 
@@ -279,7 +301,7 @@ __global__ void __launch_bounds__(THREADS)
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
-    halo_done(hs, hs_want);
+    halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -291,7 +313,7 @@ __global__ void __launch_bounds__(THREADS)
     int r0, row_end;
     block_rows(rr, THREADS, r0, row_end);
     const int row = r0 + threadIdx.x;
-    const sparsh_u64 hs_want = halo_wait(hs);
+    const HaloTurn hs_turn = halo_wait(hs);
     double contrib = 0.0;
     if (row < row_end) {
         const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
@@ -302,7 +324,7 @@ __global__ void __launch_bounds__(THREADS)
         contrib = epi_store<EPI>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
-    halo_done(hs, hs_want);
+    halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -317,7 +339,7 @@ __global__ void __launch_bounds__(256)
     block_rows(rr, ROWS_PER_CTA, r0, row_end);
     const int row = r0 + threadIdx.x / LANES;
     const bool active = row < row_end;
-    const sparsh_u64 hs_want = halo_wait(hs);
+    const HaloTurn hs_turn = halo_wait(hs);
     double s = 0.0;
     EpiRegs e;
     if (active) {
@@ -331,7 +353,7 @@ __global__ void __launch_bounds__(256)
     double contrib = 0.0;
     if (active && lane == 0) contrib = epi_store<EPI>(args, e, s, y, row);
     if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
-    halo_done(hs, hs_want);
+    halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------

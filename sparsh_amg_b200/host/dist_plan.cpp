@@ -136,19 +136,6 @@ void build_op(int nrow_g, const int *rp, const int *ci, const double *v, const d
         }
         if (diag) op.diag[k] = diag[g];
     }
-    // longest run of rows that touch no halo entry: computed while the exchange is in flight
-    int best_b = 0, best_e = 0, run_b = 0;
-    for (int k = 0; k <= op.nrow; k++) {
-        if (k == op.nrow || boundary[k]) {
-            if (k - run_b > best_e - best_b) {
-                best_b = run_b;
-                best_e = k;
-            }
-            run_b = k + 1;
-        }
-    }
-    op.ib = best_b;
-    op.ie = best_e;
     // what the others need from me: columns I own that appear in rows owned by q != rank
     std::vector<std::pair<int, int>> need;
 #pragma omp parallel num_threads(options().threads)
@@ -179,6 +166,23 @@ void build_op(int nrow_g, const int *rp, const int *ci, const double *v, const d
     op.send_idx.resize(need.size());
     for (size_t h = 0; h < need.size(); h++) op.send_idx[h] = cs.loc[need[h].second];
     (void)nranks;
+    // square operators (A): a row whose value a neighbour needs also counts as boundary, so that the fused Jacobi
+    // kernel that computes the boundary strips is the one that stores those values into the neighbours
+    if (&rs == &cs)
+        for (int k : op.send_idx) boundary[k] = 1;
+    // longest run of rows that touch no halo entry (and feed none): computed while the exchange is in flight
+    int best_b = 0, best_e = 0, run_b = 0;
+    for (int k = 0; k <= op.nrow; k++) {
+        if (k == op.nrow || boundary[k]) {
+            if (k - run_b > best_e - best_b) {
+                best_b = run_b;
+                best_e = k;
+            }
+            run_b = k + 1;
+        }
+    }
+    op.ib = best_b;
+    op.ie = best_e;
 }
 
 void transpose_csr(int nrow, int ncol, const int *rp, const int *ci, const double *v, std::vector<int> &trp,
