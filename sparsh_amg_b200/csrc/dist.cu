@@ -90,7 +90,8 @@ __device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
 __device__ __forceinline__ void spin_until(const u64 *p, u64 want, int *err) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > 4000000000ll) {
+        if (*reinterpret_cast<volatile int *>(err) != 0) break;
+        if (clock64() - t0 > 1000000000ll) {  // ~0.5 s
             atomicExch(err, 1);
             break;
         }

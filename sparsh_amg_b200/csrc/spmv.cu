@@ -73,7 +73,9 @@ struct HaloTurn {
 __device__ __forceinline__ void spin_ge(const sparsh_u64 *p, sparsh_u64 v, int *err) {
     const long long t0 = clock64();
     while (ld_acquire_sys_u64(p) < v) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s: report instead of hanging the GPU
+        // a broken handshake must never hang the GPU: give up after ~0.5 s, and at once if somebody already did
+        if (*reinterpret_cast<volatile int *>(err) != 0) break;
+        if (clock64() - t0 > 1000000000ll) {
             atomicExch(err, 1);
             break;
         }
@@ -90,7 +92,10 @@ __device__ __forceinline__ HaloTurn halo_wait(const HaloSync &hs) {
     if (hs.nsend > 0) t.prev = *reinterpret_cast<const volatile sparsh_u64 *>(hs.seq);
     const int tid = threadIdx.x;
     if (tid < hs.nnbr) spin_ge(hs.flag_local[tid], t.want, hs.err);                          // slices have landed
-    if (tid >= 8 && tid - 8 < hs.nsend) spin_ge(hs.ack_local[tid - 8], t.prev, hs.err);      // old slices consumed
+    // The fused push writes into the ping-pong partner of the vector being read, whose halo segment last held slice
+    // prev-1 (slice prev is the one this very kernel consumes): everything up to prev-1 must have been consumed.
+    // Waiting for slice prev itself would deadlock — both neighbours only ack it when this sweep ends.
+    if (tid >= 8 && tid - 8 < hs.nsend) spin_ge(hs.ack_local[tid - 8], t.prev > 0 ? t.prev - 1 : 0, hs.err);
     __syncthreads();
     return t;
 }
