@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--ref-iters", type=int, default=2, help="PCG iterations per bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tail-threshold", type=int, default=300000,
+    ap.add_argument("--tail-threshold", type=int, default=1100000,
                     help="N>1: levels with at most this many rows are replicated on every GPU instead of partitioned")
     ap.add_argument("--halo-mode", type=int, default=1, help="N>1: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv")
     ap.add_argument("--profile", action="store_true",

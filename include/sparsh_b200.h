@@ -230,6 +230,8 @@ int sparsh_dist_hierarchy_create(int n_dist_levels, const sparsh_dist_level_desc
                                  const sparsh_params *params, sparsh_dist_t *out);
 int sparsh_dist_hierarchy_destroy(sparsh_dist_t h);
 int sparsh_dist_local_rows(sparsh_dist_t h, int level, int *nrow);
+/* borrow this rank's row block of A_level (columns are [owned | halo] positions) for per-kernel measurements */
+int sparsh_dist_level_matrix(sparsh_dist_t h, int level, sparsh_matrix_t *A);
 /* y_local = A_level x (x_local: owned entries only; the halo exchange happens inside) */
 int sparsh_dist_spmv(sparsh_dist_t h, int level, const double *d_x_local, double *d_y_local);
 int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_local, int cycles, int x_is_zero);

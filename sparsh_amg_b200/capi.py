@@ -95,6 +95,7 @@ SIGNATURES = {
     "sparsh_dist_hierarchy_create": (_i, [_i, _vp, _i, _vp, c_int_p, c_int_p, _vp, _vpp]),
     "sparsh_dist_hierarchy_destroy": (_i, [_vp]),
     "sparsh_dist_local_rows": (_i, [_vp, _i, c_int_p]),
+    "sparsh_dist_level_matrix": (_i, [_vp, _i, _vpp]),
     "sparsh_dist_spmv": (_i, [_vp, _i, _vp, _vp]),
     "sparsh_dist_vcycle": (_i, [_vp, _vp, _vp, _i, _i]),
     "sparsh_dist_pcg": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),

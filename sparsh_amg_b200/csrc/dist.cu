@@ -7,11 +7,12 @@
 //   * halo exchange, halo_mode 1 (default): every vector that can receive halo data lives in one cudaMalloc'ed ARENA per
 //     rank that all ranks map through CUDA IPC.  The packing kernel stores the boundary entries STRAIGHT INTO THE
 //     NEIGHBOUR'S HALO SEGMENT over NVLink (peer stores), fences, and raises a sequence flag in the neighbour's memory;
-//     the consumer runs its interior rows meanwhile, then a one-warp kernel waits on the flags (acquire, system scope)
-//     before the boundary rows run, and an ack flag travelling the other way protects the segment against being
-//     overwritten early.  Sequence counters live in device memory, so the whole exchange replays inside a CUDA graph and
-//     no NCCL call, host round trip or extra copy sits on the exchange path (~28 us per ncclSend/ncclRecv group ->
-//     a few us);
+//     the consumer's boundary-strip kernel (rows that read the halo) waits on those flags at CTA start (acquire,
+//     system scope) and acks from its last CTA, while the interior rows run concurrently on the main stream.  For Jacobi
+//     sweeps the exchange disappears into the compute kernel altogether: the boundary-strip kernel stores each new
+//     value it produces BOTH locally and into the neighbour's halo segment of the next sweep's input vector and signals
+//     when done (fused compute + communication over peer memory).  Sequence counters live in device memory, so all of
+//     it replays inside a CUDA graph: no NCCL call, host round trip or staging copy sits on the exchange path;
 //   * halo_mode 0: pack kernel -> grouped ncclSend/ncclRecv into the halo tail on a communication stream (fallback);
 //   * Krylov scalars: local fixed-tree partial -> ncclAllReduce(sum) of 1-2 doubles, in place in device memory;
 //   * small levels: gathered once per cycle with ncclAllGather and solved redundantly on every GPU by the single-GPU
@@ -865,6 +866,12 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
 int sparsh_dist_local_rows(sparsh_dist_t h, int level, int *nrow) {
     SP_REQUIRE(h != nullptr && level >= 0 && level <= (int)h->lev.size(), "bad level");
     *nrow = level < (int)h->lev.size() ? h->lev[level].n : h->n_own_tail0;
+    return SPARSH_OK;
+}
+
+int sparsh_dist_level_matrix(sparsh_dist_t h, int level, sparsh_matrix_t *A) {
+    SP_REQUIRE(h != nullptr && level >= 0 && level < (int)h->lev.size() && A, "bad level");
+    *A = h->lev[level].A.M;
     return SPARSH_OK;
 }
 

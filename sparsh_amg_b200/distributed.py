@@ -27,7 +27,7 @@ def _np(ptr, n, dtype):
 
 
 class DistPlan:
-    def __init__(self, amg, nranks, rank, tail_threshold=300000):
+    def __init__(self, amg, nranks, rank, tail_threshold=1100000):
         self.lib = host.load()
         self.lib.sparsh_host_dist_plan.restype = C.c_void_p
         self.lib.sparsh_host_dist_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -98,6 +98,14 @@ class DistHierarchy:
     def vcycle(self, b, x, cycles=1, x_is_zero=False):
         check(self.lib.sparsh_dist_vcycle(self.h, b.ptr, x.ptr, cycles, int(bool(x_is_zero))))
         return x
+
+    def level_matrix(self, level):
+        """borrowed local block of A_level (columns = [owned | halo])"""
+        from .device import DeviceMatrix
+
+        a = C.c_void_p()
+        check(self.lib.sparsh_dist_level_matrix(self.h, level, C.byref(a)))
+        return DeviceMatrix(handle=a.value, owned=False)
 
     def pcg(self, b, x, tol, max_iter=1000):
         hist = np.zeros(max_iter + 1)
@@ -215,6 +223,21 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
 
+    # roofline of the dominant kernel on this rank's row block of the finest level (Jacobi sweep, no exchange), timed
+    # alone with CUDA events on the same stream; max over ranks
+    A0 = dH.level_matrix(0)
+    xa, xb2 = DeviceVector(A0.ncol + 8).fill(0.5), DeviceVector(A0.ncol + 8).fill(0.0)
+    reps = 20
+    lib.sparsh_jacobi(A0.h, db.ptr, xa.ptr, xb2.ptr, 0.66667, 4)
+    j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    j0.record(stream)
+    lib.sparsh_jacobi(A0.h, db.ptr, xa.ptr, xb2.ptr, 0.66667, reps)
+    j1.record(stream)
+    j1.synchronize()
+    t_j = torch.tensor([j0.elapsed_time(j1) * 1e-3 / reps], device=device, dtype=torch.float64)
+    dist.all_reduce(t_j, op=dist.ReduceOp.MAX)
+    jac_bytes_local = 12 * A0.nnz + 4 * (A0.nrow + 1) + 32 * A0.nrow
+
     # true residual of the assembled solution, checked on rank 0's host (outside every timed region)
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=device))
@@ -252,9 +275,12 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
                 "e2e": {"value": float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8,
                         "d2h_bytes_per_step": n * 8},
                 "gpu_launches": int(launches) * world,
-                "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                             "frac": None, "traffic": None,
-                             "note": "per-kernel roofline is reported by the N=1 run; at N>1 see ms_per_pcg_iteration"},
+                "roofline": {"bound": "hbm", "kernel": "csr_stream_kernel<256,EPI_JACOBI> on one rank's row block of "
+                                                      "level 0 (per GPU)",
+                             "achieved": jac_bytes_local / float(t_j.item()) / 1e9, "peak": peak,
+                             "peak_kind": peak_kind, "unit": "GB/s",
+                             "frac": jac_bytes_local / float(t_j.item()) / 1e9 / peak, "traffic": None,
+                             "bytes_per_launch": jac_bytes_local, "ms_per_launch": float(t_j.item()) * 1e3},
                 "cpu_baseline": None, "clocks": clocks}
         print(json.dumps(line), flush=True)
     shutdown(dist, plan)
