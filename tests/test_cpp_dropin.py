@@ -1,0 +1,49 @@
+"""The drop-in claim, literally: a C++ caller written against the reference's API (examples/dropin_main.cpp, same
+flow as the reference's main.cpp) compiles and links against host/AMG.hpp + our two libraries (CPU test), and on a GPU
+reproduces the reference's iteration counts on the bundled fixture."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import ROOT
+
+EXE = os.path.join(ROOT, "examples", "dropin_main")
+
+
+def build():
+    lib = os.path.join(ROOT, "sparsh_amg_b200", "lib")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "sparsh_amg_b200", "host"),
+           os.path.join(ROOT, "examples", "dropin_main.cpp"), "-o", EXE, "-L", lib, "-lsparsh_amg", "-lsparsh_b200",
+           f"-Wl,-rpath,{lib}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_reference_style_caller_compiles_and_links():
+    build()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_reference_style_caller_runs(tmp_path, fixture_system, golden):
+    build()
+    A, b = fixture_system
+    mf, rf = tmp_path / "matrix.txt", tmp_path / "rhs.txt"
+    rows = np.repeat(np.arange(A.nrow), np.diff(A.rowptr))
+    with open(mf, "w") as f:  # the reference's two-file format (src/AMG_file_read.cpp:39-72)
+        f.write(f"{A.nrow} {A.ncol} {A.nnz}\n")
+        f.write("".join(f"{r}\t{c}\t{v!r}\t\n" for r, c, v in zip(rows.tolist(), A.colindex.tolist(), A.val.tolist())))
+    with open(rf, "w") as f:
+        f.write(f"{A.nrow}\n" + "\n".join(repr(float(v)) for v in b) + "\n")
+    out = subprocess.run([EXE, str(mf), str(rf)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    rep = dict(re.findall(r"REPORT (\w+) iterations=(\d+)", out.stdout))
+    assert f"Matrix Size\t{A.nrow}" in out.stdout
+    want_amg = len(golden["fixture"]["AMG_Solver_CPU_baseline"]["hist"])  # 30
+    assert int(rep["AMG_Solver_CPU_GPU_CI"]) == want_amg
+    assert int(rep["AMG_Solver_CPU_GPU_MI"]) == want_amg
+    assert int(rep["AMG_Solver_CPU_baseline"]) == want_amg
+    assert int(rep["Solver_PCG_4"]) == len(golden["fixture"]["Solver_PCG_1"]["hist"])      # 13
+    assert int(rep["Solver_PBiCG_4"]) == len(golden["fixture"]["Solver_PBiCG_1"]["hist"])  # 7
