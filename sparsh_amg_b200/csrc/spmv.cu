@@ -159,7 +159,7 @@ __device__ __forceinline__ EpiRegs epi_load(const EpiArgs &a, const double *y, i
 }
 
 // returns this row's contribution to the fused reduction (0 when the epilogue has none)
-template <int EPI>
+template <int EPI, bool PUSH>
 __device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, double s, double *y, int row) {
     if (EPI == EPI_SPMV) {
         y[row] = s;
@@ -169,7 +169,7 @@ __device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, 
         double h = __dsub_rn(e.b, s);
         const double v = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
         y[row] = v;
-        if (a.pm_ptr) {  // fused halo push: the neighbours' next sweep reads this entry
+        if (PUSH && a.pm_ptr) {  // fused halo push: the neighbours' next sweep reads this entry
             for (int k = a.pm_ptr[row]; k < a.pm_ptr[row + 1]; k++) a.pm_dst[a.pm_nbr[k]][a.pm_off[k]] = v;
         }
     } else if (EPI == EPI_PROLONG) {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(1024) finalize_partials_kernel(const double *_
 // ---------------------------------------------------------------------------------------------------------
 // STREAM kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int THREADS, int EPI>
+template <int THREADS, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_stream_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, int cap, double *partials,
                       HaloSync hs) {
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(THREADS)
         hi = A.rowptr[row + 1];
         e = epi_load<EPI>(args, y, row);
     }
-    const HaloTurn hs_turn = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed (no-op otherwise)
+    HaloTurn hs_turn;
+    if (DIST) hs_turn = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed
     __syncthreads();  // barrier init and s_a0 visible to everyone
     mbar_wait(&bar, 0);
 
@@ -303,22 +304,23 @@ __global__ void __launch_bounds__(THREADS)
             for (int j = 0; j < 8; j++)
                 if (k + j < hi - a0) s = __dadd_rn(s, __dmul_rn(v[j], xv[j]));
         }
-        contrib = epi_store<EPI>(args, e, s, y, row);
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
-    halo_done(hs, hs_turn);
+    if (DIST) halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // SCALAR kernel: thread per row, rows of 1-2 entries (aggregation P / R): global loads are already coalesced
 // ---------------------------------------------------------------------------------------------------------
-template <int THREADS, int EPI>
+template <int THREADS, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_scalar_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
     int r0, row_end;
     block_rows(rr, THREADS, r0, row_end);
     const int row = r0 + threadIdx.x;
-    const HaloTurn hs_turn = halo_wait(hs);
+    HaloTurn hs_turn;
+    if (DIST) hs_turn = halo_wait(hs);
     double contrib = 0.0;
     if (row < row_end) {
         const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
@@ -326,16 +328,16 @@ __global__ void __launch_bounds__(THREADS)
         double s = 0.0;
         for (int k = lo; k < hi; k++)
             s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
-        contrib = epi_store<EPI>(args, e, s, y, row);
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
-    halo_done(hs, hs_turn);
+    if (DIST) halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // VECTOR kernel: LANES lanes per row, fixed shuffle tree
 // ---------------------------------------------------------------------------------------------------------
-template <int LANES, int EPI>
+template <int LANES, int EPI, bool DIST>
 __global__ void __launch_bounds__(256)
     csr_vector_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
     constexpr int ROWS_PER_CTA = 256 / LANES;
@@ -344,7 +346,8 @@ __global__ void __launch_bounds__(256)
     block_rows(rr, ROWS_PER_CTA, r0, row_end);
     const int row = r0 + threadIdx.x / LANES;
     const bool active = row < row_end;
-    const HaloTurn hs_turn = halo_wait(hs);
+    HaloTurn hs_turn;
+    if (DIST) hs_turn = halo_wait(hs);
     double s = 0.0;
     EpiRegs e;
     if (active) {
@@ -356,9 +359,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LANES);
     double contrib = 0.0;
-    if (active && lane == 0) contrib = epi_store<EPI>(args, e, s, y, row);
+    if (active && lane == 0) contrib = epi_store<EPI, DIST>(args, e, s, y, row);
     if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
-    halo_done(hs, hs_turn);
+    if (DIST) halo_done(hs, hs_turn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -368,6 +371,7 @@ struct LaunchDesc {
     RowRange rr;
     int rows1, rows2;
     HaloSync hs;
+    bool dist = false;  // multi-GPU variant of the kernel (handshake + fused push compiled in)
 };
 
 static int grid_for(LaunchDesc &d, int rows_per_cta) {
@@ -394,7 +398,9 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     Context &c = ctx();
     static bool attr_set = false;
     if (!attr_set) {
-        SP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<THREADS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<THREADS, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<THREADS, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
         attr_set = true;
     }
@@ -406,7 +412,10 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_stream_kernel<THREADS, EPI><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
+    if (d.dist)
+        csr_stream_kernel<THREADS, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
+    else
+        csr_stream_kernel<THREADS, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
     return finish_launch<EPI>(grid, args);
 }
 
@@ -418,7 +427,10 @@ static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, c
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_scalar_kernel<256, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    if (d.dist)
+        csr_scalar_kernel<256, EPI, true><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    else
+        csr_scalar_kernel<256, EPI, false><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
     return finish_launch<EPI>(grid, args);
 }
 
@@ -430,7 +442,10 @@ static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, c
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
-    csr_vector_kernel<LANES, EPI><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    if (d.dist)
+        csr_vector_kernel<LANES, EPI, true><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+    else
+        csr_vector_kernel<LANES, EPI, false><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
     return finish_launch<EPI>(grid, args);
 }
 
@@ -468,6 +483,7 @@ int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, c
     d.rows1 = e1 > b1 ? e1 - b1 : 0;
     d.rows2 = e2 > b2 ? e2 - b2 : 0;
     if (hs) d.hs = *hs;
+    d.dist = d.hs.nnbr > 0 || d.hs.nsend > 0;
     if (d.hs.nnbr > 0 && d.rows1 + d.rows2 <= 0) {
         set_error("halo handshake attached to an empty launch");
         return SPARSH_ERR_INVALID;
