@@ -589,7 +589,13 @@ int sparsh_dist_init(const char *id128, int nranks, int rank) {
     SP_NCCL(ncclCommInitRank(&m.comm, nranks, id, rank));
     m.nranks = nranks;
     m.rank = rank;
-    SP_CUDA(cudaStreamCreateWithFlags(&m.comm_stream, cudaStreamNonBlocking));
+    {
+        // the auxiliary stream runs the boundary strips (which feed the neighbours): highest priority, so their CTAs
+        // are scheduled ahead of the interior rows that share the GPU with them
+        int lo = 0, hi = 0;
+        SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SP_CUDA(cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, hi));
+    }
     SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
     SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
     return SPARSH_OK;
@@ -621,7 +627,13 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
     Comm &m = comm();
     SP_REQUIRE(m.comm != nullptr || m.nranks == 1, "sparsh_dist_init has not been called");
     if (!m.comm_stream) {  // single-rank use without NCCL (tests): still needs the stream/event plumbing
-        SP_CUDA(cudaStreamCreateWithFlags(&m.comm_stream, cudaStreamNonBlocking));
+        {
+        // the auxiliary stream runs the boundary strips (which feed the neighbours): highest priority, so their CTAs
+        // are scheduled ahead of the interior rows that share the GPU with them
+        int lo = 0, hi = 0;
+        SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SP_CUDA(cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, hi));
+    }
         SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
         SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
     }
