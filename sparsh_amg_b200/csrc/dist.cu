@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -371,7 +372,13 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
     if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
     // (the fused reductions need one grid over all rows, and tiny interiors are not worth a separate launch)
-    const bool split = !reduces && op.ie - op.ib >= 4096 && (op.ib > 0 || op.ie < op.nrow);
+    // splitting buys overlap of the handshake with the interior rows but costs a second launch and a stream fork/join:
+    // worth it only when the interior kernel is long enough (SPARSH_SPLIT_MIN_ROWS overrides the default)
+    static const int split_min = [] {
+        const char *e = getenv("SPARSH_SPLIT_MIN_ROWS");
+        return e ? atoi(e) : 4096;
+    }();
+    const bool split = !reduces && op.ie - op.ib >= split_min && (op.ib > 0 || op.ie < op.nrow);
     if (!h->peer) {
         SP_TRY(nccl_start(op, x));
         if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
