@@ -16,7 +16,7 @@ c_dbl_p = C.POINTER(C.c_double)
 
 SPARSH_OK = 0
 SPARSH_ERR_NOT_CONVERGED = 3
-KIND_SCALAR, KIND_STREAM, KIND_VECTOR = 0, 1, 2
+KIND_SCALAR, KIND_STREAM, KIND_VECTOR, KIND_DICT = 0, 1, 2, 3
 
 
 class SparshError(RuntimeError):

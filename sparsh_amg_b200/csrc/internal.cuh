@@ -62,7 +62,17 @@ constexpr int RED_MAX_BLOCKS = 1 << 20;  // partial sums per reduced value (2^28
 constexpr int RED_MAX_VALUES = 4;
 
 // ---- device CSR ---------------------------------------------------------------------------------------
-enum KernelKind { KIND_SCALAR = 0, KIND_STREAM = 1, KIND_VECTOR = 2 };
+enum KernelKind { KIND_SCALAR = 0, KIND_STREAM = 1, KIND_VECTOR = 2, KIND_DICT = 3 };
+
+// csr-dict16: lossless re-encoding of a CSR whose entries take at most 256 distinct values and 256 distinct column
+// offsets (col - row) — stencil-like matrices and their Galerkin coarsenings.  One 16-bit code per entry
+// (value id << 8 | offset id) replaces the 8-byte value and the 4-byte column: 2 B/nnz instead of 12.
+struct DictView {
+    const unsigned short *__restrict__ code;
+    const double *__restrict__ val;  // n_val distinct values
+    const int *__restrict__ off;     // n_off distinct col-row offsets
+    int n_val, n_off;
+};
 
 struct CsrView {
     int nrow, ncol, nnz;
@@ -87,7 +97,14 @@ struct sparsh_matrix_s {
     double mean_row = 0.0;
     int win128 = 0, win256 = 0;  // max nnz over any window of 128 / 256 consecutive rows
     int smem_bytes = 0;          // dynamic shared memory of the stream kernel
+    // csr-dict16 twin (present when the dictionaries fit; see DictView)
+    unsigned short *code = nullptr;
+    double *dict_val = nullptr;
+    int *dict_off = nullptr;
+    int n_dval = 0, n_doff = 0;
+    bool has_dict = false;
     sparsh::CsrView view() const { return sparsh::CsrView{nrow, ncol, nnz, rowptr, col, val}; }
+    sparsh::DictView dict() const { return sparsh::DictView{code, dict_val, dict_off, n_dval, n_doff}; }
 };
 
 namespace sparsh {

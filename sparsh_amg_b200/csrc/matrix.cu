@@ -2,6 +2,8 @@
 // Replaces class sp_matrix_gpu (reference include/AMG_gpu_matrix.hpp:10-48, src/AMG_gpu_matrix.cu:26-142).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "internal.cuh"
@@ -76,6 +78,59 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
     return SPARSH_OK;
 }
 
+// csr-dict16 twin: dictionaries of the distinct values and of the distinct (col - row) offsets, one 16-bit code per
+// entry.  Returns false (and uploads nothing) when either dictionary would need more than 256 entries.
+bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v) {
+    const char *env = getenv("SPARSH_DICT");
+    if (env && atoi(env) == 0) return false;
+    const int n = A->nrow;
+    const size_t nnz = (size_t)A->nnz;
+    if (nnz == 0) return false;
+    std::vector<double> dv;
+    std::vector<int> dof;
+    std::vector<unsigned short> code(nnz);
+    int last_v = 0, last_o = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const double val = v[j];
+            const int off = ci[j] - i;
+            int vi = -1, oi = -1;
+            if (!dv.empty() && std::memcmp(&dv[last_v], &val, sizeof val) == 0) vi = last_v;
+            for (int k = 0; vi < 0 && k < (int)dv.size(); k++)
+                if (std::memcmp(&dv[k], &val, sizeof val) == 0) vi = k;  // bit pattern: -0.0 and NaNs stay themselves
+            if (vi < 0) {
+                if (dv.size() == 256) return false;
+                dv.push_back(val);
+                vi = (int)dv.size() - 1;
+            }
+            if (!dof.empty() && dof[last_o] == off) oi = last_o;
+            for (int k = 0; oi < 0 && k < (int)dof.size(); k++)
+                if (dof[k] == off) oi = k;
+            if (oi < 0) {
+                if (dof.size() == 256) return false;
+                dof.push_back(off);
+                oi = (int)dof.size() - 1;
+            }
+            last_v = vi;
+            last_o = oi;
+            code[j] = (unsigned short)((vi << 8) | oi);
+        }
+    const size_t pad = ((nnz + 7) & ~(size_t)7) + 16;  // bulk copies round the slice outwards to multiples of 8 codes
+    cudaStream_t st = ctx().stream;
+    if (cudaMalloc(&A->code, sizeof(unsigned short) * pad) != cudaSuccess) return false;
+    cudaMalloc(&A->dict_val, sizeof(double) * 256);
+    cudaMalloc(&A->dict_off, sizeof(int) * 256);
+    cudaMemsetAsync(A->code, 0, sizeof(unsigned short) * pad, st);
+    cudaMemcpyAsync(A->code, code.data(), sizeof(unsigned short) * nnz, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(A->dict_val, dv.data(), sizeof(double) * dv.size(), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(A->dict_off, dof.data(), sizeof(int) * dof.size(), cudaMemcpyHostToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+    A->n_dval = (int)dv.size();
+    A->n_doff = (int)dof.size();
+    A->has_dict = true;
+    return true;
+}
+
 int validate(int nrow, int ncol, int nnz, const int *rp, const int *ci) {
     SP_REQUIRE(nrow >= 0 && ncol >= 0 && nnz >= 0, "negative matrix dimension");
     SP_REQUIRE(rp != nullptr, "rowptr is NULL");
@@ -104,6 +159,8 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
         sparsh_matrix_destroy(A);
         return rc;
     }
+    // matrices that would run the stream kernel get the compressed twin when their dictionaries fit
+    if (A->kind == KIND_STREAM && build_dict(A, h_rowptr, h_colindex, h_val)) A->kind = KIND_DICT;
     *out = A;
     return SPARSH_OK;
 }
@@ -134,6 +191,9 @@ int sparsh_matrix_destroy(sparsh_matrix_t A) {
     cudaFree(A->col);
     cudaFree(A->val);
     cudaFree(A->diag);
+    cudaFree(A->code);
+    cudaFree(A->dict_val);
+    cudaFree(A->dict_off);
     delete A;
     return SPARSH_OK;
 }
@@ -151,6 +211,8 @@ int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, in
     if (kind) *kind = A->kind;
     if (threads_or_lanes) *threads_or_lanes = A->kind == KIND_VECTOR ? A->lanes : A->threads;
     if (smem_bytes) *smem_bytes = A->kind == KIND_STREAM ? A->smem_bytes : 0;
+    if (smem_bytes && A->kind == KIND_DICT)
+        *smem_bytes = ((((A->threads == 256 ? A->win256 : A->win128) + 16) + 7) & ~7) * 2 + A->n_dval * 8 + A->n_doff * 4;
     return SPARSH_OK;
 }
 
@@ -167,6 +229,11 @@ int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int tl) {
         A->kind = kind;
         A->threads = tl;
         A->smem_bytes = smem;
+    } else if (kind == KIND_DICT) {
+        SP_REQUIRE(A->has_dict, "dict kernel: this matrix has no csr-dict16 twin (more than 256 distinct values or offsets)");
+        SP_REQUIRE(tl == 128 || tl == 256, "dict kernel: threads must be 128 or 256");
+        A->kind = kind;
+        A->threads = tl;
     } else if (kind == KIND_VECTOR) {
         SP_REQUIRE(tl == 2 || tl == 4 || tl == 8 || tl == 16 || tl == 32, "vector kernel: lanes must be 2..32");
         A->kind = kind;

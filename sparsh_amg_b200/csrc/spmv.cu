@@ -311,6 +311,82 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DICT kernel: the stream kernel on the csr-dict16 twin.  The CTA's slice of 16-bit codes arrives by one TMA bulk
+// copy (2 B/nnz of HBM traffic instead of 12), the two small dictionaries sit in shared memory, and thread t walks
+// row t exactly as before — same values, same order, same unfused arithmetic: results stay bit-identical.
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS, int EPI, bool DIST>
+__global__ void __launch_bounds__(THREADS)
+    csr_dict_kernel(CsrView A, DictView D, const double *x, double *y, EpiArgs args, RowRange rr, int cap,
+                    double *partials, HaloSync hs) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned short *scode = reinterpret_cast<unsigned short *>(smem_raw);
+    double *sdv = reinterpret_cast<double *>(smem_raw + (size_t)cap * sizeof(unsigned short));
+    int *sdo = reinterpret_cast<int *>(sdv + D.n_val);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_a0;
+
+    const int tid = threadIdx.x;
+    int r0, row_end;
+    block_rows(rr, THREADS, r0, row_end);
+    const int nrows = min(THREADS, row_end - r0);
+
+    if (tid == 0) {
+        const int nz0 = A.rowptr[r0], nz1 = A.rowptr[r0 + nrows];
+        const int a0 = nz0 & ~7;        // code + a0 is 16-byte aligned
+        const int a1 = (nz1 + 7) & ~7;  // the code array is padded past nnz (matrix.cu)
+        const int cnt = a1 - a0;
+        s_a0 = a0;
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        if (cnt > 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)cnt * 2u);
+            bulk_g2s(scode, D.code + a0, (uint32_t)cnt * 2u, &bar);
+        } else {
+            mbar_arrive(&bar);
+        }
+    }
+    for (int i = tid; i < D.n_val; i += THREADS) sdv[i] = D.val[i];
+    for (int i = tid; i < D.n_off; i += THREADS) sdo[i] = D.off[i];
+    int lo = 0, hi = 0;
+    EpiRegs e;
+    const int row = r0 + tid;
+    const bool active = tid < nrows;
+    if (active) {
+        lo = A.rowptr[row];
+        hi = A.rowptr[row + 1];
+        e = epi_load<EPI>(args, y, row);
+    }
+    HaloTurn hs_turn;
+    if (DIST) hs_turn = halo_wait(hs);
+    __syncthreads();  // barrier init, s_a0 and the dictionaries visible to everyone
+    mbar_wait(&bar, 0);
+
+    double contrib = 0.0;
+    if (active) {
+        const int a0 = s_a0;
+        double s = 0.0;
+        for (int k = lo - a0; k < hi - a0; k += 8) {
+            double v[8], xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ok = k + j < hi - a0;
+                const unsigned int code = ok ? scode[k + j] : 0u;
+                v[j] = ok ? sdv[code >> 8] : 0.0;
+                const int c = ok ? row + sdo[code & 255u] : 0;
+                xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (k + j < hi - a0) s = __dadd_rn(s, __dmul_rn(v[j], xv[j]));
+        }
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
+    }
+    if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
+    if (DIST) halo_done(hs, hs_turn);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // SCALAR kernel: thread per row, rows of 1-2 entries (aggregation P / R): global loads are already coalesced
 // ---------------------------------------------------------------------------------------------------------
 template <int THREADS, int EPI, bool DIST>
@@ -419,6 +495,30 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     return finish_launch<EPI>(grid, args);
 }
 
+template <int THREADS, int EPI>
+static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
+    Context &c = ctx();
+    static bool attr_set = false;
+    if (!attr_set) {
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const int win = THREADS == 256 ? A->win256 : A->win128;
+    const int cap = ((win + 16) + 7) & ~7;
+    const size_t smem = (size_t)cap * 2 + (size_t)A->n_dval * 8 + (size_t)A->n_doff * 4 + 16;
+    const int grid = grid_for(d, THREADS);
+    if (grid > RED_MAX_BLOCKS) {
+        set_error("matrix too large for the reduction workspace");
+        return SPARSH_ERR_INVALID;
+    }
+    if (d.dist)
+        csr_dict_kernel<THREADS, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+    else
+        csr_dict_kernel<THREADS, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+    return finish_launch<EPI>(grid, args);
+}
+
 template <int EPI>
 static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
@@ -460,6 +560,8 @@ static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, cons
             return launch_scalar<EPI>(A, x, y, args, d);
         case KIND_STREAM:
             return A->threads == 128 ? launch_stream<128, EPI>(A, x, y, args, d) : launch_stream<256, EPI>(A, x, y, args, d);
+        case KIND_DICT:
+            return A->threads == 128 ? launch_dict<128, EPI>(A, x, y, args, d) : launch_dict<256, EPI>(A, x, y, args, d);
         default:
             switch (A->lanes) {
                 case 2:

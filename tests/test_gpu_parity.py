@@ -91,7 +91,7 @@ def test_level_ops_match_oracle(sp, oracle, fixture_hierarchies, coarsening, kna
 
 def test_default_kernel_selection(sp, oracle):
     A = oracle.gen_poisson3d(20, 20, 20)
-    assert sp.DeviceMatrix.from_csr(A).kernel()[0] == sp.capi.KIND_STREAM
+    assert sp.DeviceMatrix.from_csr(A).kernel()[0] == sp.capi.KIND_DICT  # 2 distinct values, 7 distinct offsets
     nc, agg = oracle.hem(A, 0)
     P = CSR(A.nrow, nc, np.arange(A.nrow + 1, dtype=np.int32), agg, np.ones(A.nrow))
     assert sp.DeviceMatrix.from_csr(P).kernel()[0] == sp.capi.KIND_SCALAR
@@ -105,6 +105,49 @@ def test_default_kernel_selection(sp, oracle):
     assert dM.kernel()[0] == sp.capi.KIND_VECTOR
     x = np.random.default_rng(1).standard_normal(n)
     rel_close(dM.spmv(sp.DeviceVector(data=x)).download(), oracle.spmv(M, x), 1e-12)
+
+
+def test_fixture_matrix_keeps_plain_csr(sp, fixture_system):
+    """the bundled FE matrix has ~80k distinct values: no csr-dict16 twin, plain TMA-staged stream kernel"""
+    A, _ = fixture_system
+    dA = sp.DeviceMatrix.from_csr(A)
+    assert dA.kernel()[0] == sp.capi.KIND_STREAM
+    with pytest.raises(sp.SparshError):
+        dA.force_kernel(sp.capi.KIND_DICT, 256)
+
+
+@pytest.mark.parametrize("coarsening", [0, 1])
+@pytest.mark.parametrize("threads", [128, 256])
+def test_dict_format_is_bit_identical(sp, oracle, coarsening, threads):
+    """csr-dict16 (2 B/nnz) against the oracle AND against the plain stream kernel on every level of a Poisson
+    hierarchy: lossless re-encoding, same summation order -> identical bits."""
+    A = oracle.gen_poisson3d(24, 20, 18)
+    H = OracleAmg(A, coarsening=coarsening, limit_upper=300, limit_lower=150).hierarchy()
+    rng = np.random.default_rng(17)
+    used = 0
+    for L in H.levels:
+        M, diag = L["A"], L["diag"]
+        dA = sp.DeviceMatrix.from_csr(M, diag=diag)
+        if dA.kernel()[0] != sp.capi.KIND_DICT:
+            continue
+        used += 1
+        x, b = rng.standard_normal(M.nrow), rng.standard_normal(M.nrow)
+        dx, db = sp.DeviceVector(data=x), sp.DeviceVector(data=b)
+        res = {}
+        for kind, tl in [(sp.capi.KIND_DICT, threads), (sp.capi.KIND_STREAM, threads)]:
+            dA.force_kernel(kind, tl)
+            y, pdot = dA.spmv_dot(dx)
+            res[kind] = (dA.spmv(dx).download(), dA.residual(db, dx).download(),
+                         dA.jacobi(db, sp.DeviceVector(data=x), OMEGA, 7).download(), y.download(), pdot,
+                         dA.residual_norm(db, dx))
+        want = (oracle.spmv(M, x), oracle.store_residual(M, b, x), oracle.jacobi(M, diag, b, x, OMEGA, 6),
+                oracle.spmv(M, x))
+        for got_d, got_s, w in zip(res[sp.capi.KIND_DICT][:4], res[sp.capi.KIND_STREAM][:4], want):
+            np.testing.assert_array_equal(got_d, w)
+            np.testing.assert_array_equal(got_d, got_s)
+        assert res[sp.capi.KIND_DICT][4] == res[sp.capi.KIND_STREAM][4]  # fused dot: same partials, same tree
+        assert res[sp.capi.KIND_DICT][5] == res[sp.capi.KIND_STREAM][5]
+    assert used >= 2
 
 
 def test_edge_cases(sp, oracle):

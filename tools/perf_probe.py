@@ -60,7 +60,8 @@ def main():
     lib = sp.capi.load()
     fams = [("default", None, None)]
     if args.families == "all":
-        fams += [("stream256", 1, 256), ("stream128", 1, 128), ("vector4", 2, 4), ("vector8", 2, 8), ("scalar", 0, 256)]
+        fams += [("dict256", 3, 256), ("dict128", 3, 128), ("stream256", 1, 256), ("stream128", 1, 128),
+                 ("vector4", 2, 4), ("scalar", 0, 256)]
     for name, kind, tl in fams:
         if kind is not None:
             dA.force_kernel(kind, tl)
