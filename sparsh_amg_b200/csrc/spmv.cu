@@ -315,10 +315,13 @@ __global__ void __launch_bounds__(THREADS)
 // copy (2 B/nnz of HBM traffic instead of 12), the two small dictionaries sit in shared memory, and thread t walks
 // row t exactly as before — same values, same order, same unfused arithmetic: results stay bit-identical.
 // ---------------------------------------------------------------------------------------------------------
-template <int THREADS, int EPI, bool DIST>
+template <int THREADS, int RPT, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_dict_kernel(CsrView A, DictView D, const double *x, double *y, EpiArgs args, RowRange rr, int cap,
                     double *partials, HaloSync hs) {
+    // One CTA owns THREADS*RPT consecutive rows, thread t the rows r0 + s*THREADS + t (s < RPT).  With 2 B/nnz a
+    // 256-row tile is only ~4 KB of matrix: a CTA must own several tiles' worth of rows, or the fixed cost of a CTA
+    // (row pointer fetch -> bulk copy -> wait) caps the bytes in flight per SM below what saturates HBM.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned short *scode = reinterpret_cast<unsigned short *>(smem_raw);
     double *sdv = reinterpret_cast<double *>(smem_raw + (size_t)cap * sizeof(unsigned short));
@@ -328,8 +331,8 @@ __global__ void __launch_bounds__(THREADS)
 
     const int tid = threadIdx.x;
     int r0, row_end;
-    block_rows(rr, THREADS, r0, row_end);
-    const int nrows = min(THREADS, row_end - r0);
+    block_rows(rr, THREADS * RPT, r0, row_end);
+    const int nrows = min(THREADS * RPT, row_end - r0);
 
     if (tid == 0) {
         const int nz0 = A.rowptr[r0], nz1 = A.rowptr[r0 + nrows];
@@ -348,14 +351,19 @@ __global__ void __launch_bounds__(THREADS)
     }
     for (int i = tid; i < D.n_val; i += THREADS) sdv[i] = D.val[i];
     for (int i = tid; i < D.n_off; i += THREADS) sdo[i] = D.off[i];
-    int lo = 0, hi = 0;
-    EpiRegs e;
-    const int row = r0 + tid;
-    const bool active = tid < nrows;
-    if (active) {
-        lo = A.rowptr[row];
-        hi = A.rowptr[row + 1];
-        e = epi_load<EPI>(args, y, row);
+    // every per-row operand of all RPT rows is requested before anything is waited for
+    int lo[RPT], hi[RPT];
+    EpiRegs e[RPT];
+#pragma unroll
+    for (int s = 0; s < RPT; s++) {
+        lo[s] = 0;
+        hi[s] = 0;
+        if (s * THREADS + tid < nrows) {
+            const int row = r0 + s * THREADS + tid;
+            lo[s] = A.rowptr[row];
+            hi[s] = A.rowptr[row + 1];
+            e[s] = epi_load<EPI>(args, y, row);
+        }
     }
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);
@@ -363,24 +371,29 @@ __global__ void __launch_bounds__(THREADS)
     mbar_wait(&bar, 0);
 
     double contrib = 0.0;
-    if (active) {
-        const int a0 = s_a0;
-        double s = 0.0;
-        for (int k = lo - a0; k < hi - a0; k += 8) {
-            double v[8], xv[8];
+    const int a0 = s_a0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool ok = k + j < hi - a0;
-                const unsigned int code = ok ? scode[k + j] : 0u;
-                v[j] = ok ? sdv[code >> 8] : 0.0;
-                const int c = ok ? row + sdo[code & 255u] : 0;
-                xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+    for (int s = 0; s < RPT; s++) {
+        if (s * THREADS + tid < nrows) {
+            const int row = r0 + s * THREADS + tid;
+            double sum = 0.0;
+            for (int k = lo[s] - a0; k < hi[s] - a0; k += 8) {
+                double v[8], xv[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool ok = k + j < hi[s] - a0;
+                    const unsigned int code = ok ? scode[k + j] : 0u;
+                    v[j] = ok ? sdv[code >> 8] : 0.0;
+                    const int c = ok ? row + sdo[code & 255u] : 0;
+                    xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (k + j < hi[s] - a0) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
             }
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (k + j < hi - a0) s = __dadd_rn(s, __dmul_rn(v[j], xv[j]));
+            // reduction contributions are added in row order within the thread: still a fixed tree
+            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row));
         }
-        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -495,27 +508,33 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     return finish_launch<EPI>(grid, args);
 }
 
+constexpr int DICT_RPT = 4;  // rows per thread of the csr-dict16 kernel
+
 template <int THREADS, int EPI>
 static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
     static bool attr_set = false;
     if (!attr_set) {
-        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, DICT_RPT, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, DICT_RPT, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    const int win = THREADS == 256 ? A->win256 : A->win128;
+    const int win = DICT_RPT * (THREADS == 256 ? A->win256 : A->win128);  // bound for any THREADS*RPT-row window
     const int cap = ((win + 16) + 7) & ~7;
     const size_t smem = (size_t)cap * 2 + (size_t)A->n_dval * 8 + (size_t)A->n_doff * 4 + 16;
-    const int grid = grid_for(d, THREADS);
+    if (smem > 200 * 1024) {
+        set_error("csr-dict16 tile does not fit in shared memory");
+        return SPARSH_ERR_INVALID;
+    }
+    const int grid = grid_for(d, THREADS * DICT_RPT);
     if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_dict_kernel<THREADS, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        csr_dict_kernel<THREADS, DICT_RPT, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
     else
-        csr_dict_kernel<THREADS, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        csr_dict_kernel<THREADS, DICT_RPT, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
     return finish_launch<EPI>(grid, args);
 }
 
