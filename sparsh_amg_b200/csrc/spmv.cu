@@ -14,6 +14,8 @@
 //    oracle, not merely within 1e-12.
 //  * SCALAR (<= 2.5 nnz/row: aggregation P and R): thread per row straight from global memory (already coalesced).
 //  * VECTOR (irregular / long rows): 2..32 lanes per row, shuffle-tree reduction (1e-12 parity, not bit-exact).
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace sparsh {
@@ -508,34 +510,54 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     return finish_launch<EPI>(grid, args);
 }
 
-constexpr int DICT_RPT = 4;  // rows per thread of the csr-dict16 kernel
+// rows per thread of the csr-dict16 kernel (SPARSH_DICT_RPT = 2 | 4 | 8 overrides the default for experiments)
+static int dict_rpt() {
+    static const int v = [] {
+        const char *e = getenv("SPARSH_DICT_RPT");
+        const int r = e ? atoi(e) : 4;
+        return (r == 2 || r == 4 || r == 8) ? r : 4;
+    }();
+    return v;
+}
 
-template <int THREADS, int EPI>
-static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
+template <int THREADS, int RPT, int EPI>
+static int launch_dict_rpt(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
     static bool attr_set = false;
     if (!attr_set) {
-        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, DICT_RPT, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, DICT_RPT, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, RPT, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SP_CUDA(cudaFuncSetAttribute(csr_dict_kernel<THREADS, RPT, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    const int win = DICT_RPT * (THREADS == 256 ? A->win256 : A->win128);  // bound for any THREADS*RPT-row window
+    const int win = RPT * (THREADS == 256 ? A->win256 : A->win128);  // bound for any THREADS*RPT-row window
     const int cap = ((win + 16) + 7) & ~7;
     const size_t smem = (size_t)cap * 2 + (size_t)A->n_dval * 8 + (size_t)A->n_doff * 4 + 16;
     if (smem > 200 * 1024) {
         set_error("csr-dict16 tile does not fit in shared memory");
         return SPARSH_ERR_INVALID;
     }
-    const int grid = grid_for(d, THREADS * DICT_RPT);
+    const int grid = grid_for(d, THREADS * RPT);
     if (grid > RED_MAX_BLOCKS) {
         set_error("matrix too large for the reduction workspace");
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_dict_kernel<THREADS, DICT_RPT, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        csr_dict_kernel<THREADS, RPT, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
     else
-        csr_dict_kernel<THREADS, DICT_RPT, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        csr_dict_kernel<THREADS, RPT, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
     return finish_launch<EPI>(grid, args);
+}
+
+template <int THREADS, int EPI>
+static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
+    switch (dict_rpt()) {
+        case 2:
+            return launch_dict_rpt<THREADS, 2, EPI>(A, x, y, args, d);
+        case 8:
+            return launch_dict_rpt<THREADS, 8, EPI>(A, x, y, args, d);
+        default:
+            return launch_dict_rpt<THREADS, 4, EPI>(A, x, y, args, d);
+    }
 }
 
 template <int EPI>

@@ -163,7 +163,7 @@ def test_full_size_config4_27pt_diffusion_192_bicgstab(host):
     dH = amg.upload()
     n = A.nrow
     A0, _, _ = dH.level(0)
-    assert A0.kernel()[0] == sp.capi.KIND_STREAM and A0.kernel()[1] == 128
+    assert A0.kernel()[0] == sp.capi.KIND_STREAM and A0.kernel()[1] == 128  # distinct values everywhere: plain CSR
     x = np.random.default_rng(5).standard_normal(n)
     np.testing.assert_array_equal(A0.spmv(sp.DeviceVector(data=x)).download(), A.times(x))
     b = A.times(np.random.default_rng(42).random(n))  # b = A x*, x* ~ U(0,1), seed 42
