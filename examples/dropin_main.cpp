@@ -1,54 +1,53 @@
-// dropin_main.cpp — a caller written against the reference's public API only (AMG.hpp names), linked against this
-// repository's libraries instead of the reference's.  Flow of the reference's main.cpp:13-43: read the two-file COO
-// fixture, sp_matrix_fill, sp_matrix_fill_diagonal, call the solvers.  The only non-reference lines are the
-// sparsh::last_report() prints the tests parse.
+// dropin_main.cpp — a caller that uses nothing but the reference's public API (the names declared in its AMG.hpp),
+// built against this repository's host/AMG.hpp and libraries instead of the reference's.
 //
 //   g++ -std=c++17 -I sparsh_amg_b200/host examples/dropin_main.cpp -L sparsh_amg_b200/lib -lsparsh_amg -lsparsh_b200
-#include <algorithm>
+//   ./a.out matrix_poisson_P1_14401 matrix_poisson_P1rhs_14401
+//
+// It reads the two-file COO fixture, prepares the matrix the way the reference's example does (fill + diagonal), then
+// runs a table of solver entry points from the same zero initial guess.  The REPORT lines (sparsh::last_report(), an
+// addition of this library) are what tests/test_cpp_dropin.py parses.
 #include <cstdio>
-#include <iostream>
+#include <vector>
 
 #include "AMG.hpp"
 
+typedef void (*solver_fn)(sp_matrix_mg &, double *&, double *&);
+
+struct Entry {
+    const char *name;
+    solver_fn run;
+};
+
 int main(int argc, char *argv[]) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: %s matrixfile rhsfile\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <matrix file> <rhs file>\n", argv[0]);
         return 2;
     }
     sparsh::options().print_solve = 0;
     sparsh::options().print_setup = 0;
 
-    sp_matrix_mg *A = new sp_matrix_mg();
-    double *b;
-    readcoo(argv[1], argv[2], A, b);
-    double *x = new double[A->nrow]();
-    std::fill(x, x + A->nrow, 0);
-    A->sp_matrix_fill();
-    A->sp_matrix_fill_diagonal();
-    std::cout << "Matrix Size\t" << A->nrow << std::endl;
+    sp_matrix_mg *system_matrix = nullptr;
+    double *rhs = nullptr;
+    readcoo(argv[1], argv[2], system_matrix, rhs);
+    system_matrix->sp_matrix_fill();
+    system_matrix->sp_matrix_fill_diagonal();
+    std::printf("Matrix Size\t%d\n", system_matrix->nrow);
 
-    AMG_Solver_CPU_GPU_CI(*A, b, x);
-    std::printf("REPORT AMG_Solver_CPU_GPU_CI iterations=%d converged=%d\n", sparsh::last_report().iterations,
-                sparsh::last_report().converged);
-    std::fill(x, x + A->nrow, 0);
-    AMG_Solver_CPU_GPU_MI(*A, b, x);
-    std::printf("REPORT AMG_Solver_CPU_GPU_MI iterations=%d converged=%d\n", sparsh::last_report().iterations,
-                sparsh::last_report().converged);
-    std::fill(x, x + A->nrow, 0);
-    AMG_Solver_CPU_baseline(*A, b, x);
-    std::printf("REPORT AMG_Solver_CPU_baseline iterations=%d converged=%d\n", sparsh::last_report().iterations,
-                sparsh::last_report().converged);
-    std::fill(x, x + A->nrow, 0);
-    Solver_PCG_4(*A, b, x);
-    std::printf("REPORT Solver_PCG_4 iterations=%d converged=%d\n", sparsh::last_report().iterations,
-                sparsh::last_report().converged);
-    std::fill(x, x + A->nrow, 0);
-    Solver_PBiCG_4(*A, b, x);
-    std::printf("REPORT Solver_PBiCG_4 iterations=%d converged=%d\n", sparsh::last_report().iterations,
-                sparsh::last_report().converged);
-
-    A->~sp_matrix_mg();  // the reference's teardown idiom (main.cpp:40): explicit destructor, no delete
-    delete[] x;
-    delete[] b;
+    const Entry table[] = {{"AMG_Solver_CPU_GPU_CI", AMG_Solver_CPU_GPU_CI},
+                           {"AMG_Solver_CPU_GPU_MI", AMG_Solver_CPU_GPU_MI},
+                           {"AMG_Solver_CPU_baseline", AMG_Solver_CPU_baseline},
+                           {"Solver_PCG_4", Solver_PCG_4},
+                           {"Solver_PBiCG_4", Solver_PBiCG_4}};
+    std::vector<double> guess((size_t)system_matrix->nrow);
+    for (const Entry &e : table) {
+        guess.assign(guess.size(), 0.0);
+        double *x = guess.data();
+        e.run(*system_matrix, rhs, x);
+        const sparsh::Report &rep = sparsh::last_report();
+        std::printf("REPORT %s iterations=%d converged=%d\n", e.name, rep.iterations, rep.converged);
+    }
+    system_matrix->~sp_matrix_mg();  // explicit destructor without delete: the reference's teardown idiom is tolerated
+    delete[] rhs;
     return 0;
 }

@@ -34,7 +34,8 @@ def load():
         vp = C.c_void_p
         lib.sparsh_host_set_option.argtypes = [C.c_char_p, C.c_double]
         for f in ("sparsh_host_matrix_poisson3d", "sparsh_host_matrix_poisson2d", "sparsh_host_matrix_diffusion27",
-                  "sparsh_host_matrix_from_csr", "sparsh_host_matrix_read", "sparsh_host_amg_setup",
+                  "sparsh_host_matrix_from_csr", "sparsh_host_matrix_read", "sparsh_host_matrix_read_mm",
+                  "sparsh_host_amg_setup",
                   "sparsh_host_amg_device"):
             getattr(lib, f).restype = vp
         lib.sparsh_host_matrix_poisson3d.argtypes = [C.c_int] * 3
@@ -42,6 +43,7 @@ def load():
         lib.sparsh_host_matrix_diffusion27.argtypes = [C.c_int] * 3 + [C.c_uint]
         lib.sparsh_host_matrix_from_csr.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]
         lib.sparsh_host_matrix_read.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(c_dbl_p)]
+        lib.sparsh_host_matrix_read_mm.argtypes = [C.c_char_p]
         lib.sparsh_host_free_array.argtypes = [c_dbl_p]
         lib.sparsh_host_matrix_prepare.argtypes = [vp]
         lib.sparsh_host_matrix_free.argtypes = [vp]
@@ -130,6 +132,14 @@ class HostMatrix:
         b = np.ctypeslib.as_array(bp, shape=(M.nrow,)).copy()
         lib.sparsh_host_free_array(bp)
         return M, b
+
+    @classmethod
+    def read_matrix_market(cls, path):
+        """standard MatrixMarket coordinate file (1-based; general, symmetric or pattern)"""
+        h = load().sparsh_host_matrix_read_mm(os.fsencode(path))
+        if not h:
+            raise capi.SparshError(f"{path}: not a readable MatrixMarket coordinate file")
+        return cls(h)
 
     def times(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

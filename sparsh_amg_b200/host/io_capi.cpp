@@ -7,6 +7,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -66,6 +67,81 @@ void read_coo_new_format(char *matrixfile, sp_matrix_mg *&A, double *&b) {
     read_triplets(in, A, nrow, ncol, nnz);
     b = new double[(size_t)nrow]();
     for (int i = 0; i < nrow; i++) in >> b[i];
+}
+
+// Real MatrixMarket coordinate files: 1-based indices, entries in any order, `symmetric` files store one
+// triangle.  The reference's read_coo_new_format parses the banner but ignores `symmetric` and assumes 0-based sorted
+// input (src/AMG_file_read.cpp:74-185); this reader does what the format says.  Duplicates are summed, columns sorted.
+sp_matrix_mg *read_matrix_market(const char *path) {
+    std::ifstream in(path);
+    if (!in) return nullptr;
+    std::string line;
+    std::getline(in, line);
+    std::string lower(line);
+    std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (lower.find("%%matrixmarket") != 0 || lower.find("coordinate") == std::string::npos) return nullptr;
+    const bool symmetric = lower.find("symmetric") != std::string::npos;
+    const bool pattern = lower.find("pattern") != std::string::npos;
+    while (std::getline(in, line))
+        if (!line.empty() && line[0] != '%') break;
+    long nrow = 0, ncol = 0, nent = 0;
+    std::istringstream(line) >> nrow >> ncol >> nent;
+    std::vector<int> ri, ci;
+    std::vector<double> vv;
+    ri.reserve((size_t)nent * (symmetric ? 2 : 1));
+    ci.reserve(ri.capacity());
+    vv.reserve(ri.capacity());
+    for (long k = 0; k < nent; k++) {
+        long r = 0, c = 0;
+        double v = 1.0;
+        in >> r >> c;
+        if (!pattern) in >> v;
+        if (!in || r < 1 || c < 1 || r > nrow || c > ncol) return nullptr;
+        ri.push_back((int)r - 1);
+        ci.push_back((int)c - 1);
+        vv.push_back(v);
+        if (symmetric && r != c) {
+            ri.push_back((int)c - 1);
+            ci.push_back((int)r - 1);
+            vv.push_back(v);
+        }
+    }
+    // COO -> CSR (stable counting sort by row), then sort each row by column and merge duplicates
+    const size_t m = ri.size();
+    std::vector<int> rp((size_t)nrow + 1, 0);
+    for (size_t k = 0; k < m; k++) rp[ri[k] + 1]++;
+    for (long i = 0; i < nrow; i++) rp[i + 1] += rp[i];
+    std::vector<int> cur(rp.begin(), rp.end() - 1), cc(m);
+    std::vector<double> cv(m);
+    for (size_t k = 0; k < m; k++) {
+        const int d = cur[ri[k]]++;
+        cc[d] = ci[k];
+        cv[d] = vv[k];
+    }
+    std::vector<int> orp((size_t)nrow + 1, 0), occ;
+    std::vector<double> ocv;
+    occ.reserve(m);
+    ocv.reserve(m);
+    std::vector<int> idx;
+    for (long i = 0; i < nrow; i++) {
+        idx.resize((size_t)(rp[i + 1] - rp[i]));
+        for (size_t t = 0; t < idx.size(); t++) idx[t] = rp[i] + (int)t;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cc[a] < cc[b]; });
+        for (size_t t = 0; t < idx.size(); t++) {
+            if (t > 0 && cc[idx[t]] == occ.back())
+                ocv.back() += cv[idx[t]];
+            else {
+                occ.push_back(cc[idx[t]]);
+                ocv.push_back(cv[idx[t]]);
+            }
+        }
+        orp[i + 1] = (int)occ.size();
+    }
+    sp_matrix_mg *A = new sp_matrix_mg((int)nrow, (int)ncol, (int)occ.size());
+    std::copy(orp.begin(), orp.end(), A->rowptr);
+    std::copy(occ.begin(), occ.end(), A->colindex);
+    std::copy(ocv.begin(), ocv.end(), A->val);
+    return A;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -212,6 +288,7 @@ void *sparsh_host_matrix_read(const char *matrixfile, const char *rhsfile, doubl
     return A;
 }
 void sparsh_host_free_array(double *p) { delete[] p; }
+void *sparsh_host_matrix_read_mm(const char *path) { return read_matrix_market(path); }
 
 void sparsh_host_matrix_prepare(void *Av) {  // what main.cpp:21-22 does before any solver call
     sp_matrix_mg *A = (sp_matrix_mg *)Av;

@@ -151,3 +151,32 @@ def test_reader_roundtrip(host, tmp_path, fixture_system):
     np.testing.assert_array_equal(bb, b[:n])
     np.testing.assert_array_equal(M.val, [v for _, _, v in keep])
     M.free()
+
+
+def test_matrix_market_reader(host, tmp_path, fixture_system):
+    """standard MatrixMarket files (1-based, unsorted, general and symmetric) — SURVEY §8f.3"""
+    import scipy.io
+    import scipy.sparse as sps
+
+    A, _ = fixture_system
+    S = A.to_scipy()[:300, :300].tocsr()
+    S.eliminate_zeros()
+    S = ((S + S.T) * 0.5).tocsr()  # exactly symmetric so that the symmetric writer keeps one triangle
+    S.sort_indices()
+    rng = np.random.default_rng(0)
+    for sym in ("general", "symmetric"):
+        path = tmp_path / f"m_{sym}.mtx"
+        coo = S.tocoo()
+        perm = rng.permutation(coo.nnz)  # entries in random order
+        scipy.io.mmwrite(str(path), sps.coo_matrix((coo.data[perm], (coo.row[perm], coo.col[perm])), shape=S.shape),
+                         symmetry=sym, precision=17)
+        M = host.HostMatrix.read_matrix_market(str(path))
+        assert (M.nrow, M.ncol, M.nnz) == (300, 300, S.nnz)
+        np.testing.assert_array_equal(M.rowptr, S.indptr)
+        np.testing.assert_array_equal(M.colindex, S.indices)
+        np.testing.assert_allclose(M.val, S.data, rtol=1e-15)
+        M.free()
+    with open(tmp_path / "bad.mtx", "w") as f:
+        f.write("not a matrix\n")
+    with pytest.raises(Exception):
+        host.HostMatrix.read_matrix_market(str(tmp_path / "bad.mtx"))
