@@ -627,10 +627,30 @@ int sparsh_dist_info(int *nranks, int *rank) {
     return SPARSH_OK;
 }
 
+static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_level_desc *lev, int ntail,
+                                const sparsh_level_desc *tail, const int *tail_counts, const int *tail_rows,
+                                const sparsh_params *params);
+
 int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int ntail, const sparsh_level_desc *tail,
                                  const int *tail_counts, const int *tail_rows, const sparsh_params *params,
                                  sparsh_dist_t *out) {
     SP_TRY(ensure_init());
+    SP_REQUIRE(nd >= 1 && ntail >= 1 && lev && tail && tail_counts && tail_rows && out, "bad distributed hierarchy description");
+    sparsh_dist_s *h = new sparsh_dist_s();
+    const int rc = build_dist_hierarchy(h, nd, lev, ntail, tail, tail_counts, tail_rows, params);
+    if (rc != SPARSH_OK) {
+        const std::string msg = sparsh_last_error();  // keep the first error: the teardown may overwrite it
+        sparsh_dist_hierarchy_destroy(h);
+        set_error(msg);
+        return rc;
+    }
+    *out = h;
+    return SPARSH_OK;
+}
+
+static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_level_desc *lev, int ntail,
+                                const sparsh_level_desc *tail, const int *tail_counts, const int *tail_rows,
+                                const sparsh_params *params) {
     Comm &m = comm();
     SP_REQUIRE(m.comm != nullptr || m.nranks == 1, "sparsh_dist_init has not been called");
     if (!m.comm_stream) {  // single-rank use without NCCL (tests): still needs the stream/event plumbing
@@ -644,8 +664,6 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
         SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
         SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
     }
-    SP_REQUIRE(nd >= 1 && ntail >= 1 && lev && tail && tail_counts && tail_rows && out, "bad distributed hierarchy description");
-    sparsh_dist_s *h = new sparsh_dist_s();
     if (params)
         h->prm = *params;
     else
@@ -842,7 +860,6 @@ int sparsh_dist_hierarchy_create(int nd, const sparsh_dist_level_desc *lev, int 
         SP_NCCL(ncclAllReduce(h->d_sc, h->d_sc, 1, ncclDouble, ncclSum, m.comm, ctx().stream));
         SP_CUDA(cudaStreamSynchronize(ctx().stream));
     }
-    *out = h;
     return SPARSH_OK;
 }
 
