@@ -318,6 +318,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tail-threshold", type=int, default=1100000,
                     help="N>1: levels with at most this many rows are replicated on every GPU instead of partitioned")
+    ap.add_argument("--share-hierarchy", action="store_true",
+                    help="N>1: rank 0 builds the host hierarchy once, the other ranks map it (needed beyond 256^3)")
     ap.add_argument("--halo-mode", type=int, default=1, help="N>1: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: honour --warmup/--max-iter literally, do not insist on convergence")

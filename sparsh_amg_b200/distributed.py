@@ -154,13 +154,34 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
     host.set_options(threads=threads, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=1,
                      halo_mode=args.halo_mode)
     t0 = time.time()
-    A = host.HostMatrix.poisson3d(grid, grid, grid)
-    amg = host.HostAmg(A)  # every rank builds the (sequential) host hierarchy, then keeps only its part on the GPU
+    shm = None
+    if getattr(args, "share_hierarchy", False):
+        # rank 0 builds the hierarchy once and publishes it as files; the others map it read-only (host/share.cpp).
+        # Needed beyond 256^3: at 512^3 eight private copies (8 x 35 GB) do not fit in the box's RAM.
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        shm = os.path.join(base, f"sparsh_hier_{os.environ.get('MASTER_PORT', '0')}_{grid}")
+        A = amg = None
+        if rank == 0:
+            A = host.HostMatrix.poisson3d(grid, grid, grid)
+            amg = host.HostAmg(A)
+            amg.save(shm)
+        dist.barrier()
+        if rank != 0:
+            amg = host.HostAmg.load(shm)
+    else:
+        A = host.HostMatrix.poisson3d(grid, grid, grid)
+        amg = host.HostAmg(A)  # every rank builds the (sequential) host hierarchy, keeps only its part on the GPU
     t_setup = time.time() - t0
     plan = DistPlan(amg, world, rank, tail_threshold=args.tail_threshold)
     dH = plan.upload()
+    if shm is not None:
+        dist.barrier()
+        if rank == 0:
+            import shutil
+
+            shutil.rmtree(shm, ignore_errors=True)
     n_local = dH.local_rows(0)
-    n = A.nrow
+    n = amg.level_dims(0)[0]
     rows = plan.rows(0)
     b_local = np.ones(n_local)
     tol = 1e-8 * float(np.sqrt(n))

@@ -60,6 +60,9 @@ def load():
                                                                      C.POINTER(c_dbl_p), C.POINTER(c_dbl_p),
                                                                      C.POINTER(c_int_p), C.POINTER(c_int_p),
                                                                      C.POINTER(c_dbl_p)]
+        lib.sparsh_host_amg_save.argtypes = [vp, C.c_char_p]
+        lib.sparsh_host_amg_load.restype = vp
+        lib.sparsh_host_amg_load.argtypes = [C.c_char_p]
         lib.sparsh_host_amg_upload.argtypes = [vp]
         lib.sparsh_host_amg_device.argtypes = [vp]
         lib.sparsh_host_call.argtypes = [C.c_char_p, vp, c_dbl_p, c_dbl_p]
@@ -175,6 +178,25 @@ class HostAmg:
             A._refresh()
         self.nlevels = self.lib.sparsh_host_amg_nlevels(self.h)
 
+    def save(self, directory):
+        """write every level as raw binary files under `directory` (ideally /dev/shm/...) for HostAmg.load"""
+        os.makedirs(directory, exist_ok=True)
+        rc = self.lib.sparsh_host_amg_save(self.h, os.fsencode(directory))
+        if rc != 0:
+            raise capi.SparshError(f"could not save the hierarchy to {directory} ({rc})")
+
+    @classmethod
+    def load(cls, directory):
+        """map a saved hierarchy read-only: N ranks of a node share ONE copy in the page cache (host/share.cpp)"""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.A = None
+        self.h = self.lib.sparsh_host_amg_load(os.fsencode(directory))
+        if not self.h:
+            raise capi.SparshError(f"could not map a hierarchy from {directory}")
+        self.nlevels = self.lib.sparsh_host_amg_nlevels(self.h)
+        return self
+
     def level_dims(self, k):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self.lib.sparsh_host_amg_level_dims(self.h, k, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
@@ -208,7 +230,7 @@ class HostAmg:
         d = DeviceHierarchy.__new__(DeviceHierarchy)
         d.lib = capi.load()
         d.h = self.lib.sparsh_host_amg_device(self.h)
-        d.n = self.A.nrow
+        d.n = self.level_dims(0)[0]
         d.nlevels = self.nlevels
         d.free = lambda: None  # owned by the AMG_GPU1_solver
         return d

@@ -154,7 +154,11 @@ AMG_solver::~AMG_solver() {
     torn_down = true;
     if (device) sparsh_hierarchy_destroy(device);
     device = nullptr;
-    if (Av) {
+    if (shared_mapping) {
+        // arrays belong to read-only file mappings shared between ranks: release the mappings, never delete[] into them
+        extern void sparsh_release_shared_hierarchy(AMG_solver *);
+        sparsh_release_shared_hierarchy(this);
+    } else if (Av) {
         for (int q = l; q > 0; q--) {
             if (Av[q]) {
                 delete[] Av[q]->rowptr;

@@ -179,6 +179,7 @@ class AMG_solver {
     double **Rv = nullptr;
     sparsh_hierarchy_s *device = nullptr;  // resident device hierarchy (created on first solve / GPU_Allocations)
     bool torn_down = false;
+    void *shared_mapping = nullptr;  // set when the hierarchy's arrays live in files mapped read-only (host/share.cpp)
 
     AMG_solver();
     void AMG_solver_setup_jacobi(sp_matrix_mg &A);

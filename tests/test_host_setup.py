@@ -180,3 +180,38 @@ def test_matrix_market_reader(host, tmp_path, fixture_system):
         f.write("not a matrix\n")
     with pytest.raises(Exception):
         host.HostMatrix.read_matrix_market(str(tmp_path / "bad.mtx"))
+
+
+def test_shared_hierarchy_roundtrip_and_plans(host, oracle, tmp_path):
+    """rank 0 saves, every rank maps read-only (host/share.cpp): identical levels and identical partition plans"""
+    from sparsh_amg_b200.distributed import DistPlan
+
+    host.set_options(coarse_upper=500, coarse_lower=250)
+    A = host.HostMatrix.poisson3d(18, 16, 20)
+    amg = host.HostAmg(A)
+    d = str(tmp_path / "hier")
+    amg.save(d)
+    shared = host.HostAmg.load(d)
+    assert shared.nlevels == amg.nlevels
+    for L0, L1 in zip(amg.levels(), shared.levels()):
+        for key in ("rowptr", "colindex", "val"):
+            np.testing.assert_array_equal(getattr(L0["A"], key), getattr(L1["A"], key))
+            if L0["P"] is not None:
+                np.testing.assert_array_equal(getattr(L0["P"], key), getattr(L1["P"], key))
+        np.testing.assert_array_equal(L0["diag"], L1["diag"])
+    for rank in range(3):
+        p0, p1 = DistPlan(amg, 3, rank, tail_threshold=700), DistPlan(shared, 3, rank, tail_threshold=700)
+        assert (p0.nd, p0.nlevels) == (p1.nd, p1.nlevels)
+        for l in range(p0.nd):
+            np.testing.assert_array_equal(p0.rows(l), p1.rows(l))
+            for which in "APR":
+                a, b = p0.op(l, which), p1.op(l, which)
+                for key in ("rowptr", "colindex", "val", "send_idx", "send_rank", "recv_rank", "recv_ptr", "halo_global"):
+                    np.testing.assert_array_equal(a[key], b[key])
+                assert a["interior"] == b["interior"]
+        p0.free()
+        p1.free()
+    shared.free()
+    amg.free()
+    A.free()
+    host.set_options(coarse_upper=4000, coarse_lower=2000)
