@@ -326,8 +326,14 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started without the launcher: become `torchrun --nproc-per-node N bench.py ...` (one process per GPU)
+        port = str(29500 + os.getpid() % 400)
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", port,
+                                  os.path.abspath(__file__)] + sys.argv[1:])
+    run_ours(args)
 
 
 if __name__ == "__main__":

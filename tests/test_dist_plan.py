@@ -8,7 +8,8 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("world,shape,coarsening", [(2, (20, 20, 24), 0), (3, (16, 18, 20), 0), (2, (20, 20, 24), 1)])
+@pytest.mark.parametrize("world,shape,coarsening", [(2, (20, 20, 24), 0), (3, (16, 18, 20), 0), (2, (20, 20, 24), 1),
+                                                    (8, (16, 16, 32), 0)])
 def test_partition_plans_with_gloo(world, shape, coarsening):
     port = 29500 + (os.getpid() % 2000) + world + 7 * coarsening
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
