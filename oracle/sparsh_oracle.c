@@ -622,6 +622,8 @@ typedef struct {
     int *prp, *pci;
     double *pv;
     double *X, *B, *R;
+    int total_colors;  /* SOR hierarchies only */
+    int *color_count, *perm;
 } so_level;
 
 struct so_amg {
@@ -697,6 +699,109 @@ so_amg *so_amg_setup(int n, const int *rp, const int *ci, const double *v, int c
     return h;
 }
 
+/* colour-permute level L in place (src/AMG_cpu_matrix.cpp:81-199), keeping perm and the colour offsets */
+static void level_color(so_level *L) {
+    int maxdeg = 0;
+    for (int i = 0; i < L->n; i++)
+        if (L->rp[i + 1] - L->rp[i] > maxdeg) maxdeg = L->rp[i + 1] - L->rp[i];
+    L->perm = (int *)xmalloc(sizeof(int) * (size_t)L->n);
+    L->color_count = (int *)xcalloc((size_t)maxdeg + 2, sizeof(int));
+    int *qrp, *qci;
+    double *qv;
+    L->total_colors = so_color_reorder(L->n, L->rp, L->ci, L->v, L->perm, L->color_count, &qrp, &qci, &qv);
+    free(L->rp);
+    free(L->ci);
+    free(L->v);
+    L->rp = qrp;
+    L->ci = qci;
+    L->v = qv;
+    so_fill_diagonal(L->n, L->rp, L->ci, L->v, L->diag);
+}
+
+/* src/AMG_phases.cpp:94-147 */
+so_amg *so_amg_setup_sor(int n, const int *rp, const int *ci, const double *v, int max_levels, int limit_upper,
+                         int limit_lower) {
+    so_amg *h = (so_amg *)xcalloc(1, sizeof(so_amg));
+    h->omega = 0.66667;
+    h->smooth_iter = 6;
+    if (max_levels > SO_MAXLEV) max_levels = SO_MAXLEV;
+    int l = 0;
+    level_set_matrix(&h->lev[0], n, rp, ci, v, 1);
+    sort_columns(n, h->lev[0].rp, h->lev[0].ci, h->lev[0].v);
+    level_color(&h->lev[0]); /* :108 */
+    while (h->lev[l].n > limit_upper && l < max_levels - 1) { /* :109 */
+        so_level *F = &h->lev[l];
+        int *agg = (int *)xmalloc(sizeof(int) * (size_t)F->n);
+        F->pncol = so_hem(F->n, F->rp, F->ci, F->v, l, agg); /* :118, on the permuted matrix */
+        F->prp = (int *)xmalloc(sizeof(int) * ((size_t)F->n + 1));
+        F->pv = (double *)xmalloc(sizeof(double) * (size_t)F->n);
+        for (int i = 0; i <= F->n; i++) F->prp[i] = i;
+        for (int i = 0; i < F->n; i++) F->pv[i] = 1.0;
+        F->pci = agg;
+        F->pnnz = F->n;
+        int *crp, *cci;
+        double *cv;
+        so_rap(F->n, F->rp, F->ci, F->v, F->pncol, F->prp, F->pci, F->pv, &crp, &cci, &cv); /* :124 */
+        l = l + 1;
+        level_set_matrix(&h->lev[l], F->pncol, crp, cci, cv, 0);
+        level_color(&h->lev[l]); /* :125-126 */
+        /* reorder_prolongator (:128): column c of P becomes inv[c] of the coarse permutation */
+        {
+            so_level *C = &h->lev[l];
+            int *inv = (int *)xmalloc(sizeof(int) * (size_t)C->n);
+            for (int i = 0; i < C->n; i++) inv[C->perm[i]] = i;
+            for (int j = 0; j < F->pnnz; j++) F->pci[j] = inv[F->pci[j]];
+            free(inv);
+            sort_columns(F->n, F->prp, F->pci, F->pv);
+        }
+        if (h->lev[l].n < limit_lower) break; /* :135 */
+    }
+    h->l = l;
+    h->lu = so_lu_factor(h->lev[l].n, h->lev[l].rp, h->lev[l].ci, h->lev[l].v); /* :146 */
+    return h;
+}
+
+static double level0_residual(so_amg *h);
+
+/* src/AMG_phases.cpp:279-297, one cycle */
+static void one_cycle_sor(so_amg *h) {
+    int l = h->l;
+    for (int l1 = 0; l1 < l; l1++) {
+        so_level *F = &h->lev[l1], *C = &h->lev[l1 + 1];
+        so_sor_multicolor(F->n, F->rp, F->ci, F->v, F->diag, F->color_count, F->total_colors, F->B, F->X, F->helper,
+                          h->omega, 6);                                                          /* :281 */
+        so_store_residual(F->n, F->rp, F->ci, F->v, F->B, F->X, F->R);                           /* :282 */
+        so_transfer_residual(F->n, F->pncol, F->prp, F->pci, F->pv, F->R, C->B);                 /* :283 */
+        memset(C->X, 0, sizeof(double) * (size_t)C->n);                                          /* :284 */
+    }
+    so_lu_solve(h->lu, h->lev[l].B, h->lev[l].X); /* :289 */
+    for (int l1 = l; l1 > 0; l1--) {
+        so_level *F = &h->lev[l1 - 1], *C = &h->lev[l1];
+        so_transfer_solution(F->n, F->prp, F->pci, F->pv, C->X, F->X);                           /* :294 */
+        so_sor_multicolor(F->n, F->rp, F->ci, F->v, F->diag, F->color_count, F->total_colors, F->B, F->X, F->helper,
+                          h->omega, 6);                                                          /* :295 */
+    }
+}
+
+int so_amg_solve_sor(so_amg *h, const double *b, double *x, double tol, int max_cycles, double *hist) {
+    so_level *L = &h->lev[0];
+    for (int i = 0; i < L->n; i++) { /* reorder_rhs: b <- b[perm] (src/AMG_main_solvers.cpp:35) */
+        L->B[i] = b[L->perm[i]];
+        L->X[i] = x[L->perm[i]];
+    }
+    double r1 = level0_residual(h); /* :242 */
+    int cycles = 0;
+    if (hist) hist[0] = r1;
+    while (r1 > tol && cycles < max_cycles) { /* :277 */
+        one_cycle_sor(h);
+        cycles++;
+        r1 = level0_residual(h); /* :300 */
+        if (hist) hist[cycles] = r1;
+    }
+    for (int i = 0; i < L->n; i++) x[L->perm[i]] = L->X[i];
+    return cycles;
+}
+
 so_amg *so_amg_from_levels(int nlevels, const int *nrow, const int *const *rp, const int *const *ci,
                            const double *const *v, const int *pncol, const int *const *prp, const int *const *pci,
                            const double *const *pv) {
@@ -738,6 +843,8 @@ void so_amg_free(so_amg *h) {
         free(L->X);
         free(L->B);
         free(L->R);
+        free(L->color_count);
+        free(L->perm);
     }
     so_lu_free(h->lu);
     free(h);

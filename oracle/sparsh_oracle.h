@@ -108,6 +108,16 @@ int so_cg(int n, const int *rp, const int *ci, const double *v, const double *b,
 int so_bicgstab(int n, const int *rp, const int *ci, const double *v, const double *b, double *x, double tol,
                 int max_iter, double *hist);
 
+/* AMG_solver_setup_SOR (src/AMG_phases.cpp:94-147): every level colour-permuted (color_matrix_and_reorder), P columns
+ * re-labelled by the coarse permutation (reorder_prolongator, src/AMG_cycle_utilities.cpp:149-188). */
+so_amg *so_amg_setup_sor(int n, const int *rp, const int *ci, const double *v, int max_levels, int limit_upper,
+                         int limit_lower);
+/* AMG_Solver_2 (src/AMG_main_solvers.cpp:30-43) = reorder_rhs + AMG_solve_SOR(b,x,-1) (src/AMG_phases.cpp:275-304):
+ * V-cycles with 6 multicolour-SOR sweeps (the literal 6 of :281,:295) until ||r|| <= tol.  b and x are in the CALLER's
+ * ordering (the reference never copies x back and permutes with the forward permutation twice — SURVEY Appendix B;
+ * the oracle returns x properly).  hist as so_amg_solve.  Returns cycles. */
+int so_amg_solve_sor(so_amg *h, const double *b, double *x, double tol, int max_cycles, double *hist);
+
 /* ---- synthetic matrices of BASELINE.json's configs; arrays malloc'ed ---- */
 void so_gen_poisson2d_5pt(int nx, int ny, int **rp, int **ci, double **v);
 void so_gen_poisson3d_7pt(int nx, int ny, int nz, int **rp, int **ci, double **v);

@@ -80,6 +80,8 @@ class Oracle:
         lib.so_free.argtypes = [C.c_void_p]
         lib.so_amg_setup.restype = C.c_void_p
         lib.so_amg_from_levels.restype = C.c_void_p
+        lib.so_amg_setup_sor.restype = C.c_void_p
+        lib.so_amg_solve_sor.argtypes = [C.c_void_p, c_dbl_p, c_dbl_p, C.c_double, C.c_int, c_dbl_p]
         for f in ("so_amg_free", "so_amg_nlevels"):
             getattr(lib, f).argtypes = [C.c_void_p]
         lib.so_amg_level_dims.argtypes = [C.c_void_p, C.c_int] + [c_int_p] * 4
@@ -211,10 +213,14 @@ class Hierarchy:
 
 
 class OracleAmg:
-    def __init__(self, A=None, coarsening=0, max_levels=32, limit_upper=4000, limit_lower=2000, hierarchy=None):
+    def __init__(self, A=None, coarsening=0, max_levels=32, limit_upper=4000, limit_lower=2000, hierarchy=None,
+                 sor=False):
         self.o = Oracle.get()
         lib = self.o.lib
-        if hierarchy is None:
+        if sor:
+            self.h = lib.so_amg_setup_sor(A.nrow, ip(A.rowptr), ip(A.colindex), dp(A.val), max_levels, limit_upper,
+                                          limit_lower)
+        elif hierarchy is None:
             self.h = lib.so_amg_setup(A.nrow, ip(A.rowptr), ip(A.colindex), dp(A.val), coarsening, max_levels,
                                       limit_upper, limit_lower)
         else:
@@ -290,6 +296,12 @@ class OracleAmg:
         x = np.empty_like(b)
         self.o.lib.so_amg_coarse_solve(self.h, dp(b), dp(x))
         return x
+
+    def solve_sor(self, b, x, tol, max_cycles=500):
+        x = x.copy()
+        hist = np.zeros(max_cycles + 1)
+        k = self.o.lib.so_amg_solve_sor(self.h, dp(b), dp(x), tol, max_cycles, dp(hist))
+        return x, hist[: k + 1]
 
     def pcg(self, b, x, tol, max_iter=500):
         x = x.copy()
