@@ -72,9 +72,20 @@ int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *h_row
 int sparsh_matrix_destroy(sparsh_matrix_t A); /* sp_matrix_gpu::~sp_matrix_gpu (src/AMG_gpu_matrix.cu:131-142) */
 int sparsh_matrix_dims(sparsh_matrix_t A, int *nrow, int *ncol, int *nnz);
 /* kernel family chosen at upload: 0 scalar (<=2.5 nnz/row), 1 stream (TMA-staged, thread per row), 2 vector
- * (sub-warp per row).  sparsh_matrix_force_kernel overrides it (tests exercise every family). */
+ * (sub-warp per row), 3 dict (stream kernel over the csr-dict16 twin below, chosen whenever the twin exists).
+ * sparsh_matrix_force_kernel overrides it (tests exercise every family). */
 int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, int *smem_bytes);
 int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int threads_or_lanes);
+
+/* csr-dict16, the lossless storage the stream kernel prefers: entry j of row i is stored as the 16-bit code
+ * (vi << 8) | oi with val[j] == dict_val[vi] (compared by bit pattern) and colindex[j] == i + dict_off[oi]; rowptr is
+ * kept.  Exists iff the matrix has <= 256 distinct values and <= 256 distinct (column - row) offsets (constant-
+ * coefficient stencils and their Galerkin coarse operators); otherwise plain CSR is used.  No counterpart in the
+ * reference (it stores CSR only, src/AMG_gpu_matrix.cu:26-102); results are bit-identical to the CSR kernels'.
+ * Host-only helper (needs no GPU), so the encoding can be checked anywhere: code[nnz], dict_val[256], dict_off[256];
+ * *n_val == 0 on return means "not representable". */
+int sparsh_dict_encode(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex, const double *h_val,
+                       unsigned short *code, double *dict_val, int *dict_off, int *n_val, int *n_off);
 
 /* ------------------------------------------------------------------ per-op ----- */
 /* K9  y = A x                              cusparseDcsrmv, e.g. src/AMG_main_solvers.cu:100,221,354 */

@@ -60,6 +60,7 @@ SIGNATURES = {
     "sparsh_matrix_dims": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_kernel": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_force_kernel": (_i, [_vp, _i, _i]),
+    "sparsh_dict_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p]),
     "sparsh_spmv": (_i, [_vp, _vp, _vp]),
     "sparsh_spmv_dot": (_i, [_vp, _vp, _vp, _vp]),
     "sparsh_residual": (_i, [_vp, _vp, _vp, _vp]),

@@ -79,16 +79,9 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
 }
 
 // csr-dict16 twin: dictionaries of the distinct values and of the distinct (col - row) offsets, one 16-bit code per
-// entry.  Returns false (and uploads nothing) when either dictionary would need more than 256 entries.
-bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v) {
-    const char *env = getenv("SPARSH_DICT");
-    if (env && atoi(env) == 0) return false;
-    const int n = A->nrow;
-    const size_t nnz = (size_t)A->nnz;
-    if (nnz == 0) return false;
-    std::vector<double> dv;
-    std::vector<int> dof;
-    std::vector<unsigned short> code(nnz);
+// entry.  The encoder is host-only; false when either dictionary would need more than 256 entries.
+bool dict_encode(int n, const int *rp, const int *ci, const double *v, unsigned short *code, std::vector<double> &dv,
+                 std::vector<int> &dof) {
     int last_v = 0, last_o = 0;
     for (int i = 0; i < n; i++)
         for (int j = rp[i]; j < rp[i + 1]; j++) {
@@ -115,6 +108,20 @@ bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *
             last_o = oi;
             code[j] = (unsigned short)((vi << 8) | oi);
         }
+    return true;
+}
+
+// encodes and uploads; false (nothing uploaded) when the matrix is not representable or SPARSH_DICT=0
+bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v) {
+    const char *env = getenv("SPARSH_DICT");
+    if (env && atoi(env) == 0) return false;
+    const int n = A->nrow;
+    const size_t nnz = (size_t)A->nnz;
+    if (nnz == 0) return false;
+    std::vector<double> dv;
+    std::vector<int> dof;
+    std::vector<unsigned short> code(nnz);
+    if (!dict_encode(n, rp, ci, v, code.data(), dv, dof)) return false;
     const size_t pad = ((nnz + 7) & ~(size_t)7) + 16;  // bulk copies round the slice outwards to multiples of 8 codes
     cudaStream_t st = ctx().stream;
     if (cudaMalloc(&A->code, sizeof(unsigned short) * pad) != cudaSuccess) return false;
@@ -165,6 +172,21 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
         A->threads = 128;  // measured on B200 (256^3 Jacobi): 128-thread CTAs x 4 rows per thread 0.180 ms, 256 x 4 0.199 ms
     }
     *out = A;
+    return SPARSH_OK;
+}
+
+int sparsh_dict_encode(int nrow, int ncol, int nnz, const int *rp, const int *ci, const double *v,
+                       unsigned short *code, double *dict_val, int *dict_off, int *n_val, int *n_off) {
+    SP_TRY(validate(nrow, ncol, nnz, rp, ci));
+    SP_REQUIRE(code && dict_val && dict_off && n_val && n_off, "output pointer is NULL");
+    std::vector<double> dv;
+    std::vector<int> dof;
+    *n_val = *n_off = 0;
+    if (!dict_encode(nrow, rp, ci, v, code, dv, dof)) return SPARSH_OK;  // not representable: plain CSR is used
+    std::copy(dv.begin(), dv.end(), dict_val);
+    std::copy(dof.begin(), dof.end(), dict_off);
+    *n_val = (int)dv.size();
+    *n_off = (int)dof.size();
     return SPARSH_OK;
 }
 

@@ -215,3 +215,53 @@ def test_shared_hierarchy_roundtrip_and_plans(host, oracle, tmp_path):
     amg.free()
     A.free()
     host.set_options(coarse_upper=4000, coarse_lower=2000)
+
+
+def _dict_encode(A):
+    import ctypes as C
+    import sparsh_amg_b200 as sp
+
+    lib = sp.capi.load()
+    code = np.zeros(max(A.nnz, 1), dtype=np.uint16)
+    dval, doff = np.zeros(256), np.zeros(256, dtype=np.int32)
+    nv, no = C.c_int(-1), C.c_int(-1)
+    rc = lib.sparsh_dict_encode(A.nrow, A.ncol, A.nnz, sp.capi.ip(A.rowptr), sp.capi.ip(A.colindex), sp.capi.dp(A.val),
+                                code.ctypes.data_as(C.c_void_p), sp.capi.dp(dval), sp.capi.ip(doff), C.byref(nv),
+                                C.byref(no))
+    assert rc == 0
+    return code, dval[: nv.value], doff[: no.value]
+
+
+def test_csr_dict16_encoding_is_lossless(host, fixture_system):
+    """The csr-dict16 twin the stream kernel runs on must decode to exactly the CSR it came from (values by bit
+    pattern), and must decline matrices whose dictionaries do not fit (they stay plain CSR)."""
+    import sparsh_amg_b200 as sp
+    from sparsh_amg_b200.generators import HostCSR, poisson_7pt
+
+    # constant-coefficient stencil and its Galerkin coarse operators
+    A = poisson_7pt(40, 36, 32)
+    amg = host.HostAmg(host.HostMatrix.from_csr(A))
+    assert amg.nlevels >= 3
+    representable = 0
+    for k, lev in enumerate(amg.levels()):
+        M = lev["A"]
+        code, dval, doff = _dict_encode(M)
+        if k == 0:
+            assert len(dval) == 2 and len(doff) == 7
+        if len(dval) == 0:
+            continue
+        representable += 1
+        rows = np.repeat(np.arange(M.nrow, dtype=np.int64), np.diff(M.rowptr))
+        assert np.array_equal(dval[code >> 8].view(np.uint64), np.ascontiguousarray(M.val).view(np.uint64))
+        assert np.array_equal(rows + doff[code & 255], M.colindex)
+    assert representable >= 2
+    # -0.0 and 0.0 are different dictionary entries (bit pattern, not ==)
+    Z = HostCSR(2, 2, [0, 1, 2], [0, 1], [0.0, -0.0])
+    code, dval, _ = _dict_encode(Z)
+    assert len(dval) == 2 and np.signbit(dval[code[1] >> 8]) and not np.signbit(dval[code[0] >> 8])
+    # more than 256 distinct values (the unstructured fixture) or offsets: not representable
+    F, _ = fixture_system
+    assert len(_dict_encode(F)[1]) == 0
+    n = 300
+    W = HostCSR(1, n, [0, n], np.arange(n), np.ones(n))
+    assert len(_dict_encode(W)[1]) == 0
