@@ -72,7 +72,8 @@ int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *h_row
 int sparsh_matrix_destroy(sparsh_matrix_t A); /* sp_matrix_gpu::~sp_matrix_gpu (src/AMG_gpu_matrix.cu:131-142) */
 int sparsh_matrix_dims(sparsh_matrix_t A, int *nrow, int *ncol, int *nnz);
 /* kernel family chosen at upload: 0 scalar (<=2.5 nnz/row), 1 stream (TMA-staged, thread per row), 2 vector
- * (sub-warp per row), 3 dict (stream kernel over the csr-dict16 twin below, chosen whenever the twin exists).
+ * (sub-warp per row), 3 dict (stream kernel over the csr-dict16 twin below, chosen whenever the twin exists),
+ * 4 pattern (csr-pattern8 twin below; built only when the environment sets SPARSH_PATTERN=1|2, selected with 1).
  * sparsh_matrix_force_kernel overrides it (tests exercise every family). */
 int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, int *smem_bytes);
 int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int threads_or_lanes);
@@ -86,6 +87,17 @@ int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int threads_or_lanes
  * *n_val == 0 on return means "not representable". */
 int sparsh_dict_encode(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex, const double *h_val,
                        unsigned short *code, double *dict_val, int *dict_off, int *n_val, int *n_off);
+
+/* csr-pattern8, one byte per ROW: rows of stencil matrices and of their Galerkin coarse operators repeat a few
+ * patterns (the ordered list of (column - row, value) pairs; 27 per level in the 7-point Poisson hierarchy).  pat[i] <
+ * 255 selects entries start[p] .. start[p+1] of the table, pat[i] == 255 is the escape: the row is evaluated from the
+ * CSR arrays, which stay resident.  Patterns are numbered by decreasing row count.  Same entries, same order, same
+ * arithmetic: bit-identical to the CSR kernels.  h_diag (may be NULL) is the diagonal the caller smooths with; rows
+ * where it differs from the tabulated diagonal become escapes.  Host-only helper (needs no GPU): pat[nrow],
+ * ent_val/ent_off[2048], start[256]; *n_pat == 0 on return means "rows do not repeat" (more than 65536 distinct rows). */
+int sparsh_pattern_encode(int nrow, int ncol, int nnz, const int *h_rowptr, const int *h_colindex,
+                          const double *h_val, const double *h_diag, unsigned char *pat, double *ent_val,
+                          int *ent_off, int *start, int *n_pat, int *n_escape);
 
 /* ------------------------------------------------------------------ per-op ----- */
 /* K9  y = A x                              cusparseDcsrmv, e.g. src/AMG_main_solvers.cu:100,221,354 */

@@ -16,7 +16,7 @@ c_dbl_p = C.POINTER(C.c_double)
 
 SPARSH_OK = 0
 SPARSH_ERR_NOT_CONVERGED = 3
-KIND_SCALAR, KIND_STREAM, KIND_VECTOR, KIND_DICT = 0, 1, 2, 3
+KIND_SCALAR, KIND_STREAM, KIND_VECTOR, KIND_DICT, KIND_PATTERN = 0, 1, 2, 3, 4
 
 
 class SparshError(RuntimeError):
@@ -60,6 +60,8 @@ SIGNATURES = {
     "sparsh_matrix_dims": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_kernel": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_force_kernel": (_i, [_vp, _i, _i]),
+    "sparsh_pattern_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p,
+                                   c_int_p]),
     "sparsh_dict_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p]),
     "sparsh_spmv": (_i, [_vp, _vp, _vp]),
     "sparsh_spmv_dot": (_i, [_vp, _vp, _vp, _vp]),

@@ -62,7 +62,7 @@ constexpr int RED_MAX_BLOCKS = 1 << 20;  // partial sums per reduced value (2^28
 constexpr int RED_MAX_VALUES = 4;
 
 // ---- device CSR ---------------------------------------------------------------------------------------
-enum KernelKind { KIND_SCALAR = 0, KIND_STREAM = 1, KIND_VECTOR = 2, KIND_DICT = 3 };
+enum KernelKind { KIND_SCALAR = 0, KIND_STREAM = 1, KIND_VECTOR = 2, KIND_DICT = 3, KIND_PATTERN = 4 };
 
 // csr-dict16: lossless re-encoding of a CSR whose entries take at most 256 distinct values and 256 distinct column
 // offsets (col - row) — stencil-like matrices and their Galerkin coarsenings.  One 16-bit code per entry
@@ -73,6 +73,28 @@ struct DictView {
     const int *__restrict__ off;     // n_off distinct col-row offsets
     int n_val, n_off;
 };
+
+// csr-pattern8: one byte per ROW.  Rows of a stencil matrix (and of its Galerkin coarsenings) repeat a handful of
+// patterns — the ordered list of (col - row offset, value) pairs; the 7-point Poisson hierarchy has 27 per level.
+// pat[i] < 255 selects a pattern of the table (entries start[p]..start[p+1]); pat[i] == 255 is the escape: that row is
+// evaluated from the plain CSR arrays, which stay resident.  Same entries, same order, same unfused arithmetic as the
+// CSR kernels: results are bit-identical.
+struct PatEntry {
+    double v;
+    int off;
+    int pad;
+};
+struct PatView {
+    const unsigned char *__restrict__ pat;  // nrow
+    const PatEntry *__restrict__ ent;       // n_ent (+8 zero entries)
+    const int *__restrict__ start;          // n_pat + 1
+    const double *__restrict__ pdiag;       // n_pat: the row's diagonal as sp_matrix_fill_diagonal extracts it
+    int n_pat, n_ent;
+    int use_pdiag;  // the epilogue's d[] is this matrix' own diagonal: take it from the table
+};
+constexpr int PAT_ESCAPE = 255;    // pattern id of an escape row
+constexpr int PAT_MAX_ENT = 2048;  // table entries over all patterns (32 KB)
+constexpr int PAT_MAX_ROW = 64;    // longer rows are never tabulated
 
 struct CsrView {
     int nrow, ncol, nnz;
@@ -103,6 +125,16 @@ struct sparsh_matrix_s {
     int *dict_off = nullptr;
     int n_dval = 0, n_doff = 0;
     bool has_dict = false;
+    // csr-pattern8 twin (see PatView)
+    unsigned char *pat = nullptr;
+    sparsh::PatEntry *pat_ent = nullptr;
+    int *pat_start = nullptr;
+    double *pat_diag = nullptr;
+    int n_pat = 0, n_pent = 0, n_escape = 0;
+    bool has_pat = false;
+    sparsh::PatView pattern(bool use_pdiag) const {
+        return sparsh::PatView{pat, pat_ent, pat_start, pat_diag, n_pat, n_pent, use_pdiag ? 1 : 0};
+    }
     sparsh::CsrView view() const { return sparsh::CsrView{nrow, ncol, nnz, rowptr, col, val}; }
     sparsh::DictView dict() const { return sparsh::DictView{code, dict_val, dict_off, n_dval, n_doff}; }
 };

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "internal.cuh"
@@ -138,6 +139,162 @@ bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *
     return true;
 }
 
+// ---- csr-pattern8 (PatView in internal.cuh) ------------------------------------------------------------------
+struct PatternTable {
+    std::vector<int> start;  // n_pat + 1
+    std::vector<double> val;
+    std::vector<int> off;
+    std::vector<double> diag;  // per pattern: first entry with offset 0 (what sp_matrix_fill_diagonal extracts), else 0
+    int n_escape = 0;
+};
+
+inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+
+// do rows ra and rb list the same (col - row, value bits) pairs in the same order?
+inline bool same_row_pattern(const int *rp, const int *ci, const double *v, int ra, int rb) {
+    const int la = rp[ra + 1] - rp[ra];
+    if (la != rp[rb + 1] - rp[rb]) return false;
+    const int a = rp[ra], b = rp[rb];
+    for (int k = 0; k < la; k++)
+        if (ci[a + k] - ra != ci[b + k] - rb || !same_bits(v[a + k], v[b + k])) return false;
+    return true;
+}
+
+inline uint64_t row_pattern_hash(const int *rp, const int *ci, const double *v, int row) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)(rp[row + 1] - rp[row]);
+    for (int k = rp[row]; k < rp[row + 1]; k++) {
+        uint64_t bits;
+        std::memcpy(&bits, &v[k], sizeof bits);
+        h = (h ^ bits) * 0x100000001B3ull;
+        h = (h ^ (uint64_t)(uint32_t)(ci[k] - row)) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
+// Host-only encoder.  pat[i] receives the pattern id of row i (PAT_ESCAPE for rows left to the CSR arrays).  Patterns
+// are numbered by decreasing row count (ties: first occurrence).  h_diag, when given, is the diagonal the caller will
+// smooth with: rows where it differs from the tabulated one become escapes.  Returns false when the matrix is not
+// stencil-like (too many distinct rows, or fewer than min_cover of the rows tabulated).
+bool pattern_encode(int n, const int *rp, const int *ci, const double *v, const double *h_diag, unsigned char *pat,
+                    PatternTable &T, double min_cover) {
+    struct Cand {
+        int rep, count;
+    };
+    constexpr size_t MAX_CAND = 1u << 16;
+    std::vector<Cand> cand;
+    std::unordered_map<uint64_t, int> by_hash;
+    std::vector<int> cand_of((size_t)n, -1);
+    int prev = -1;
+    for (int i = 0; i < n; i++) {
+        if (rp[i + 1] - rp[i] > PAT_MAX_ROW) {
+            prev = -1;
+            continue;
+        }
+        int c = -1;
+        if (prev >= 0 && same_row_pattern(rp, ci, v, i, cand[prev].rep)) {
+            c = prev;  // neighbouring rows of a stencil matrix mostly repeat the pattern
+        } else {
+            const uint64_t h = row_pattern_hash(rp, ci, v, i);
+            auto it = by_hash.find(h);
+            if (it == by_hash.end()) {
+                if (cand.size() >= MAX_CAND) return false;  // not stencil-like: stop before the map grows with n
+                c = (int)cand.size();
+                cand.push_back(Cand{i, 0});
+                by_hash.emplace(h, c);
+            } else if (same_row_pattern(rp, ci, v, i, cand[it->second].rep)) {
+                c = it->second;
+            }  // else: a hash collision between different rows; this one stays an escape
+        }
+        if (c >= 0) cand[c].count++;
+        cand_of[i] = c;
+        prev = c;
+    }
+    std::vector<int> order(cand.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return cand[a].count != cand[b].count ? cand[a].count > cand[b].count : cand[a].rep < cand[b].rep;
+    });
+    std::vector<int> id_of(cand.size(), -1);
+    T = PatternTable();
+    T.start.push_back(0);
+    for (int c : order) {
+        const int r = cand[c].rep, len = rp[r + 1] - rp[r];
+        if ((int)T.diag.size() == PAT_ESCAPE) break;
+        if ((int)T.val.size() + len > PAT_MAX_ENT) continue;
+        id_of[c] = (int)T.diag.size();
+        double d = 0.0;
+        bool found = false;
+        for (int k = rp[r]; k < rp[r + 1]; k++) {
+            T.val.push_back(v[k]);
+            T.off.push_back(ci[k] - r);
+            if (!found && ci[k] == r) {
+                d = v[k];
+                found = true;
+            }
+        }
+        T.diag.push_back(d);
+        T.start.push_back((int)T.val.size());
+    }
+    long long covered = 0;
+    for (int i = 0; i < n; i++) {
+        int id = cand_of[i] >= 0 ? id_of[cand_of[i]] : -1;
+        if (id >= 0 && h_diag && !same_bits(h_diag[i], T.diag[id])) id = -1;
+        pat[i] = (unsigned char)(id >= 0 ? id : PAT_ESCAPE);
+        covered += id >= 0;
+    }
+    T.n_escape = n - (int)covered;
+    return n > 0 && !T.diag.empty() && (double)covered >= min_cover * (double)n;
+}
+
+// SPARSH_PATTERN: 0 (default until the kernel has its B200 parity + timing runs) no twin; 1 build the twin and run the
+// pattern kernel wherever it applies; 2 build the twin but keep the default kernel (sparsh_matrix_force_kernel selects)
+int pattern_mode() {
+    const char *env = getenv("SPARSH_PATTERN");
+    return env ? atoi(env) : 0;
+}
+
+// encodes and uploads; false (nothing uploaded) when the rows do not repeat enough
+bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, const double *h_diag) {
+    const int n = A->nrow;
+    if (n == 0 || A->nnz == 0) return false;
+    std::vector<unsigned char> pat((size_t)n + 16, (unsigned char)PAT_ESCAPE);
+    PatternTable T;
+    if (!pattern_encode(n, rp, ci, v, h_diag, pat.data(), T, 0.75)) return false;
+    const int n_pat = (int)T.diag.size(), n_ent = (int)T.val.size();
+    std::vector<PatEntry> ent((size_t)n_ent + 8, PatEntry{0.0, 0, 0});
+    for (int k = 0; k < n_ent; k++) ent[k] = PatEntry{T.val[k], T.off[k], 0};
+    cudaStream_t st = ctx().stream;
+    bool ok = cudaMalloc(&A->pat, pat.size()) == cudaSuccess &&
+              cudaMalloc(&A->pat_ent, sizeof(PatEntry) * ent.size()) == cudaSuccess &&
+              cudaMalloc(&A->pat_start, sizeof(int) * ((size_t)n_pat + 1)) == cudaSuccess &&
+              cudaMalloc(&A->pat_diag, sizeof(double) * (size_t)n_pat) == cudaSuccess;
+    if (ok) {
+        cudaMemcpyAsync(A->pat, pat.data(), pat.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(A->pat_ent, ent.data(), sizeof(PatEntry) * ent.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(A->pat_start, T.start.data(), sizeof(int) * ((size_t)n_pat + 1), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(A->pat_diag, T.diag.data(), sizeof(double) * (size_t)n_pat, cudaMemcpyHostToDevice, st);
+        ok = cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaFree(A->pat);
+        cudaFree(A->pat_ent);
+        cudaFree(A->pat_start);
+        cudaFree(A->pat_diag);
+        A->pat = nullptr;
+        A->pat_ent = nullptr;
+        A->pat_start = nullptr;
+        A->pat_diag = nullptr;
+        cudaGetLastError();
+        return false;
+    }
+    A->n_pat = n_pat;
+    A->n_pent = n_ent;
+    A->n_escape = T.n_escape;
+    A->has_pat = true;
+    return true;
+}
+
 int validate(int nrow, int ncol, int nnz, const int *rp, const int *ci) {
     SP_REQUIRE(nrow >= 0 && ncol >= 0 && nnz >= 0, "negative matrix dimension");
     SP_REQUIRE(rp != nullptr, "rowptr is NULL");
@@ -171,6 +328,13 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
         A->kind = KIND_DICT;
         A->threads = 128;  // measured on B200 (256^3 Jacobi): 128-thread CTAs x 4 rows per thread 0.180 ms, 256 x 4 0.199 ms
     }
+    // ... and the per-row pattern twin when rows repeat (SPARSH_PATTERN, see pattern_mode)
+    const int pmode = pattern_mode();
+    if (pmode > 0 && (A->kind == KIND_STREAM || A->kind == KIND_DICT) && nrow == ncol &&
+        build_pattern(A, h_rowptr, h_colindex, h_val, h_diag) && pmode == 1) {
+        A->kind = KIND_PATTERN;
+        A->threads = 128;
+    }
     *out = A;
     return SPARSH_OK;
 }
@@ -187,6 +351,23 @@ int sparsh_dict_encode(int nrow, int ncol, int nnz, const int *rp, const int *ci
     std::copy(dof.begin(), dof.end(), dict_off);
     *n_val = (int)dv.size();
     *n_off = (int)dof.size();
+    return SPARSH_OK;
+}
+
+int sparsh_pattern_encode(int nrow, int ncol, int nnz, const int *rp, const int *ci, const double *v,
+                          const double *h_diag, unsigned char *pat, double *ent_val, int *ent_off, int *start,
+                          int *n_pat, int *n_escape) {
+    SP_TRY(validate(nrow, ncol, nnz, rp, ci));
+    SP_REQUIRE(pat && ent_val && ent_off && start && n_pat && n_escape, "output pointer is NULL");
+    PatternTable T;
+    *n_pat = 0;
+    *n_escape = nrow;
+    if (!pattern_encode(nrow, rp, ci, v, h_diag, pat, T, 0.0)) return SPARSH_OK;  // rows do not repeat: CSR / dict
+    std::copy(T.val.begin(), T.val.end(), ent_val);
+    std::copy(T.off.begin(), T.off.end(), ent_off);
+    std::copy(T.start.begin(), T.start.end(), start);
+    *n_pat = (int)T.diag.size();
+    *n_escape = T.n_escape;
     return SPARSH_OK;
 }
 
@@ -219,6 +400,10 @@ int sparsh_matrix_destroy(sparsh_matrix_t A) {
     cudaFree(A->code);
     cudaFree(A->dict_val);
     cudaFree(A->dict_off);
+    cudaFree(A->pat);
+    cudaFree(A->pat_ent);
+    cudaFree(A->pat_start);
+    cudaFree(A->pat_diag);
     delete A;
     return SPARSH_OK;
 }
@@ -257,6 +442,11 @@ int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int tl) {
     } else if (kind == KIND_DICT) {
         SP_REQUIRE(A->has_dict, "dict kernel: this matrix has no csr-dict16 twin (more than 256 distinct values or offsets)");
         SP_REQUIRE(tl == 128 || tl == 256, "dict kernel: threads must be 128 or 256");
+        A->kind = kind;
+        A->threads = tl;
+    } else if (kind == KIND_PATTERN) {
+        SP_REQUIRE(A->has_pat, "pattern kernel: this matrix has no csr-pattern8 twin (SPARSH_PATTERN unset, or rows do not repeat)");
+        SP_REQUIRE(tl == 128 || tl == 256, "pattern kernel: threads must be 128 or 256");
         A->kind = kind;
         A->threads = tl;
     } else if (kind == KIND_VECTOR) {

@@ -12,6 +12,8 @@
 //    Row sums are accumulated sequentially with separate mul/add (no FMA contraction), i.e. in exactly the order
 //    of the reference's CPU path (mkl_sparse_d_mv over column-sorted rows): results are bit-identical to the
 //    oracle, not merely within 1e-12.
+//  * DICT / PATTERN: the stream kernel's rows in two lossless compressed layouts (csr-dict16: 2 B per entry;
+//    csr-pattern8: 1 B per row), for matrices whose entries / rows repeat (stencils and their Galerkin coarsenings).
 //  * SCALAR (<= 2.5 nnz/row: aggregation P and R): thread per row straight from global memory (already coalesced).
 //  * VECTOR (irregular / long rows): 2..32 lanes per row, shuffle-tree reduction (1e-12 parity, not bit-exact).
 #include <cstdlib>
@@ -147,7 +149,7 @@ struct EpiRegs {
     double b, xi, d;
 };
 
-template <int EPI>
+template <int EPI, bool LOAD_D = true>
 __device__ __forceinline__ EpiRegs epi_load(const EpiArgs &a, const double *y, int row) {
     EpiRegs e;
     e.b = 0.0;
@@ -156,7 +158,7 @@ __device__ __forceinline__ EpiRegs epi_load(const EpiArgs &a, const double *y, i
     if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM) e.b = a.b[row];
     if (EPI == EPI_JACOBI || EPI == EPI_SPMV_DOT) e.xi = a.xi[row];
     if (EPI == EPI_PROLONG || EPI == EPI_SOR) e.xi = y[row];
-    if (EPI == EPI_JACOBI || EPI == EPI_SOR) e.d = a.d[row];
+    if (LOAD_D && (EPI == EPI_JACOBI || EPI == EPI_SOR)) e.d = a.d[row];
     return e;
 }
 
@@ -402,6 +404,108 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// PATTERN kernel: csr-pattern8 (PatView, internal.cuh).  One byte per row selects the row's list of (offset, value)
+// pairs in a small table that each CTA copies into shared memory (a few KB out of L2; a warp whose rows share a
+// pattern — the common case — reads each 16-byte entry as one broadcast).  No matrix stream is left to stage: per
+// row the kernel moves the pattern byte, the vector operands and the result, which is what bounds it.  Thread t owns
+// rows r0 + s*THREADS + t (s < RPT); all their pattern bytes and per-row operands are requested before the table copy
+// is waited for.  Escape rows (id 255) are walked from the resident CSR arrays.
+// ---------------------------------------------------------------------------------------------------------
+template <int THREADS, int RPT, int JB, int EPI, bool DIST>
+__global__ void __launch_bounds__(THREADS)
+    csr_pattern_kernel(CsrView A, PatView P, const double *x, double *y, EpiArgs args, RowRange rr, double *partials,
+                       HaloSync hs) {
+    constexpr bool NEEDS_D = (EPI == EPI_JACOBI || EPI == EPI_SOR);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);   // n_ent values
+    double *sdiag = sval + P.n_ent;                        // n_pat
+    int *soff = reinterpret_cast<int *>(sdiag + P.n_pat);  // n_ent offsets
+    int *sstart = soff + P.n_ent;                          // n_pat + 1
+
+    const int tid = threadIdx.x;
+    int r0, row_end;
+    block_rows(rr, THREADS * RPT, r0, row_end);
+    const int nrows = min(THREADS * RPT, row_end - r0);
+
+    int pid[RPT];
+    EpiRegs e[RPT];
+#pragma unroll
+    for (int s = 0; s < RPT; s++) {
+        pid[s] = -1;
+        if (s * THREADS + tid < nrows) {
+            const int row = r0 + s * THREADS + tid;
+            pid[s] = P.pat[row];
+            e[s] = epi_load<EPI, false>(args, y, row);
+        }
+    }
+    for (int i = tid; i < P.n_ent; i += THREADS) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(P.ent) + i);
+        sval[i] = __hiloint2double(q.y, q.x);
+        soff[i] = q.z;
+    }
+    for (int i = tid; i < P.n_pat; i += THREADS) sdiag[i] = __ldg(P.pdiag + i);
+    for (int i = tid; i <= P.n_pat; i += THREADS) sstart[i] = __ldg(P.start + i);
+    HaloTurn hs_turn;
+    if (DIST) hs_turn = halo_wait(hs);
+    __syncthreads();  // the table is in place
+
+    // The RPT rows of a thread advance together, JB entries each per step: RPT*JB independent gathers are in flight
+    // per thread instead of one row's (each row's sum still runs left to right over its own entries).
+    int st[RPT], len[RPT];
+    double sum[RPT];
+    int maxlen = 0;
+#pragma unroll
+    for (int s = 0; s < RPT; s++) {
+        st[s] = 0;
+        len[s] = 0;
+        sum[s] = 0.0;
+        if (pid[s] >= 0 && pid[s] != PAT_ESCAPE) {
+            st[s] = sstart[pid[s]];
+            len[s] = sstart[pid[s] + 1] - st[s];
+            if (NEEDS_D) e[s].d = P.use_pdiag ? sdiag[pid[s]] : args.d[r0 + s * THREADS + tid];
+        }
+        maxlen = max(maxlen, len[s]);
+    }
+    for (int k = 0; k < maxlen; k += JB) {
+        double v[RPT][JB], xv[RPT][JB];
+#pragma unroll
+        for (int s = 0; s < RPT; s++)
+#pragma unroll
+            for (int j = 0; j < JB; j++) {
+                const bool ok = k + j < len[s];
+                v[s][j] = ok ? sval[st[s] + k + j] : 0.0;
+                const int c = ok ? r0 + s * THREADS + tid + soff[st[s] + k + j] : 0;
+                xv[s][j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+            }
+#pragma unroll
+        for (int s = 0; s < RPT; s++)
+#pragma unroll
+            for (int j = 0; j < JB; j++)
+                if (k + j < len[s]) sum[s] = __dadd_rn(sum[s], __dmul_rn(v[s][j], xv[s][j]));
+    }
+
+    double contrib = 0.0;
+#pragma unroll
+    for (int s = 0; s < RPT; s++) {
+        if (pid[s] >= 0) {
+            const int row = r0 + s * THREADS + tid;
+            if (pid[s] == PAT_ESCAPE) {
+                const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
+#pragma unroll 1  // rare path: keep it out of the instruction cache's way
+                for (int k = lo; k < hi; k++)
+                    sum[s] = __dadd_rn(sum[s], __dmul_rn(__ldg(A.val + k),
+                                                         load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
+                if (NEEDS_D) e[s].d = args.d[row];
+            }
+            // reduction contributions are added in row order within the thread: still a fixed tree
+            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum[s], y, row));
+        }
+    }
+    if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
+    if (DIST) halo_done(hs, hs_turn);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // SCALAR kernel: thread per row, rows of 1-2 entries (aggregation P / R): global loads are already coalesced
 // ---------------------------------------------------------------------------------------------------------
 template <int THREADS, int EPI, bool DIST>
@@ -560,6 +664,60 @@ static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, con
     }
 }
 
+// rows per thread and entries per row per step of the csr-pattern8 kernel (SPARSH_PATTERN_RPT = 2 | 4 | 8 and
+// SPARSH_PATTERN_JB = 2 | 4 override the defaults for experiments)
+static int pattern_rpt() {
+    static const int v = [] {
+        const char *e = getenv("SPARSH_PATTERN_RPT");
+        const int r = e ? atoi(e) : 4;
+        return (r == 2 || r == 4 || r == 8) ? r : 4;
+    }();
+    return v;
+}
+static int pattern_jb() {
+    static const int v = [] {
+        const char *e = getenv("SPARSH_PATTERN_JB");
+        return (e && atoi(e) == 4) ? 4 : 2;
+    }();
+    return v;
+}
+
+template <int THREADS, int RPT, int JB, int EPI>
+static int launch_pattern_cfg(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
+    Context &c = ctx();
+    const int grid = grid_for(d, THREADS * RPT);
+    if (grid > RED_MAX_BLOCKS) {
+        set_error("matrix too large for the reduction workspace");
+        return SPARSH_ERR_INVALID;
+    }
+    const PatView P = A->pattern(args.d != nullptr && args.d == A->diag);
+    // table: n_ent values + offsets, n_pat diagonals, n_pat + 1 starts: at most 27 KB (PAT_MAX_ENT), under the 48 KB
+    // a kernel may use without opting in
+    const size_t smem = (size_t)A->n_pent * 12 + (size_t)A->n_pat * 8 + (size_t)(A->n_pat + 1) * 4;
+    if (d.dist)
+        csr_pattern_kernel<THREADS, RPT, JB, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), P, x, y, args, d.rr, c.partials, d.hs);
+    else
+        csr_pattern_kernel<THREADS, RPT, JB, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), P, x, y, args, d.rr, c.partials, d.hs);
+    return finish_launch<EPI>(grid, args);
+}
+
+template <int THREADS, int EPI>
+static int launch_pattern(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
+    const int rpt = pattern_rpt();
+    if (pattern_jb() == 4) {
+        if (rpt == 2) return launch_pattern_cfg<THREADS, 2, 4, EPI>(A, x, y, args, d);
+        return launch_pattern_cfg<THREADS, 4, 4, EPI>(A, x, y, args, d);  // 8 rows x 4 entries would spill
+    }
+    switch (rpt) {
+        case 2:
+            return launch_pattern_cfg<THREADS, 2, 2, EPI>(A, x, y, args, d);
+        case 8:
+            return launch_pattern_cfg<THREADS, 8, 2, EPI>(A, x, y, args, d);
+        default:
+            return launch_pattern_cfg<THREADS, 4, 2, EPI>(A, x, y, args, d);
+    }
+}
+
 template <int EPI>
 static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
@@ -603,6 +761,8 @@ static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, cons
             return A->threads == 128 ? launch_stream<128, EPI>(A, x, y, args, d) : launch_stream<256, EPI>(A, x, y, args, d);
         case KIND_DICT:
             return A->threads == 128 ? launch_dict<128, EPI>(A, x, y, args, d) : launch_dict<256, EPI>(A, x, y, args, d);
+        case KIND_PATTERN:
+            return A->threads == 128 ? launch_pattern<128, EPI>(A, x, y, args, d) : launch_pattern<256, EPI>(A, x, y, args, d);
         default:
             switch (A->lanes) {
                 case 2:

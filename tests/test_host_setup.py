@@ -265,3 +265,73 @@ def test_csr_dict16_encoding_is_lossless(host, fixture_system):
     n = 300
     W = HostCSR(1, n, [0, n], np.arange(n), np.ones(n))
     assert len(_dict_encode(W)[1]) == 0
+
+
+def _pattern_encode(A, diag=None):
+    import ctypes as C
+    import sparsh_amg_b200 as sp
+
+    lib = sp.capi.load()
+    pat = np.full(max(A.nrow, 1), 7, dtype=np.uint8)
+    ent_val, ent_off = np.zeros(2048), np.zeros(2048, dtype=np.int32)
+    start = np.zeros(256, dtype=np.int32)
+    n_pat, n_esc = C.c_int(-1), C.c_int(-1)
+    rc = lib.sparsh_pattern_encode(A.nrow, A.ncol, A.nnz, sp.capi.ip(A.rowptr), sp.capi.ip(A.colindex),
+                                   sp.capi.dp(A.val), None if diag is None else sp.capi.dp(diag),
+                                   pat.ctypes.data_as(C.c_void_p), sp.capi.dp(ent_val), sp.capi.ip(ent_off),
+                                   sp.capi.ip(start), C.byref(n_pat), C.byref(n_esc))
+    assert rc == 0
+    return pat, ent_val, ent_off, start[: n_pat.value + 1], n_pat.value, n_esc.value
+
+
+def _check_pattern_decode(M, pat, ent_val, ent_off, start, n_pat, n_esc):
+    """every tabulated row must decode to exactly its CSR row (order, columns, value bits)"""
+    rp = M.rowptr.astype(np.int64)
+    assert np.count_nonzero(pat == 255) == n_esc
+    assert pat[pat != 255].max(initial=0) < n_pat
+    counts = np.bincount(pat[pat != 255], minlength=n_pat)
+    assert np.all(np.diff(counts) <= 0)  # numbered by decreasing row count
+    vbits = np.ascontiguousarray(M.val).view(np.uint64)
+    for p in range(n_pat):
+        rows = np.flatnonzero(pat == p)
+        assert len(rows) > 0
+        ln = start[p + 1] - start[p]
+        assert np.all(np.diff(M.rowptr)[rows] == ln)
+        idx = rp[rows][:, None] + np.arange(ln)[None, :]
+        assert np.array_equal(M.colindex[idx], rows[:, None] + ent_off[start[p]: start[p + 1]][None, :])
+        want = np.broadcast_to(ent_val[start[p]: start[p + 1]].view(np.uint64)[None, :], idx.shape)
+        assert np.array_equal(vbits[idx], want)
+
+
+def test_csr_pattern8_encoding_is_lossless(host, fixture_system):
+    """csr-pattern8 (one byte per row): tabulated rows decode to exactly their CSR rows; rows that do not repeat, or
+    whose smoothing diagonal differs from the tabulated one, are escapes served from the CSR arrays."""
+    from sparsh_amg_b200.generators import HostCSR, poisson_7pt
+
+    A = poisson_7pt(40, 36, 32)
+    amg = host.HostAmg(host.HostMatrix.from_csr(A))
+    for k, lev in enumerate(amg.levels()):
+        M = lev["A"]
+        enc = _pattern_encode(M, np.ascontiguousarray(lev["diag"]))
+        _check_pattern_decode(M, *enc)
+        assert enc[4] == 27 and enc[5] == 0  # 3 x 3 x 3 boundary classes at every level, nothing escapes
+    # a caller-supplied diagonal that differs on some rows: exactly those rows escape
+    d = np.full(A.nrow, 6.0)
+    d[[5, 77, 1234]] = 6.5
+    pat, *_rest, n_esc = _pattern_encode(A, d)
+    assert n_esc == 3 and set(np.flatnonzero(pat == 255)) == {5, 77, 1234}
+    # a row longer than 64 entries and a unique row are escapes; the repeated rows are tabulated
+    n = 200
+    rp = np.arange(n + 1, dtype=np.int32) * 2
+    ci = np.stack([np.arange(n), (np.arange(n) + 1) % n], axis=1).astype(np.int32)
+    ci.sort(axis=1)
+    v = np.tile([2.0, -1.0], n)
+    W = HostCSR(n, n, rp, ci.ravel(), v)
+    enc = _pattern_encode(W)
+    _check_pattern_decode(W, *enc)
+    assert enc[4] == 2 and enc[5] == 0  # the wrap-around row (sorted columns: offsets 0 - (n-1), 0) is its own pattern
+    # unstructured matrix: whatever is tabulated still decodes, but almost nothing repeats (the library keeps CSR)
+    F, _ = fixture_system
+    enc = _pattern_encode(F)
+    _check_pattern_decode(F, *enc)
+    assert enc[5] > 0.25 * F.nrow

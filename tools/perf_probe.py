@@ -3,6 +3,8 @@
 Times the SpMV-family kernels and BLAS-1 on synthetic Poisson matrices with CUDA events on the library's stream and
 prints achieved algorithmic GB/s (SURVEY §8d byte model) per kernel family.  Usage:
     python tools/perf_probe.py [--n 256] [--dim 3] [--reps 20] [--families all|default]
+The experimental csr-pattern8 kernel is probed when the twin exists: run with SPARSH_PATTERN=2 (and
+SPARSH_PATTERN_RPT=2|4|8, SPARSH_PATTERN_JB=2|4 for its launch shapes).
 """
 import argparse
 import json
@@ -62,6 +64,8 @@ def main():
     if args.families == "all":
         fams += [("dict256", 3, 256), ("dict128", 3, 128), ("stream256", 1, 256), ("stream128", 1, 128),
                  ("vector4", 2, 4), ("scalar", 0, 256)]
+        if os.environ.get("SPARSH_PATTERN", "0") in ("1", "2"):
+            fams[1:1] = [("pattern128", 4, 128), ("pattern256", 4, 256)]
     for name, kind, tl in fams:
         if kind is not None:
             dA.force_kernel(kind, tl)
