@@ -239,8 +239,11 @@ def run_ours(args):
     z = A0.nnz
     kind, tl, _ = A0.kernel()
     dict_fmt = kind == sp.capi.KIND_DICT
+    pat_fmt = kind == sp.capi.KIND_PATTERN  # opt-in (SPARSH_PATTERN=1)
     jac_bytes = 12 * z + 4 * (n + 1) + 32 * n          # ALGORITHMIC bytes of the CSR operation
     jac_stored = (2 if dict_fmt else 12) * z + 4 * (n + 1) + 32 * n  # bytes the kernel actually has to move
+    if pat_fmt:
+        jac_stored = 25 * n  # pattern byte + b + x + x' per row; the diagonal comes from the pattern table
     tb = sp.DeviceVector(n)
     reps = 20
     lib.sparsh_jacobi(A0.h, db.ptr, dx.ptr, tb.ptr, 0.66667, 4)
@@ -255,7 +258,7 @@ def run_ours(args):
     traffic = None
     tf = os.path.join(ROOT, "profiles", "jacobi_dram_traffic.json")
     if os.path.exists(tf):
-        traffic = json.load(open(tf)).get(f"{grid}_dict" if dict_fmt else str(grid))
+        traffic = json.load(open(tf)).get(f"{grid}_pattern" if pat_fmt else f"{grid}_dict" if dict_fmt else str(grid))
     vbytes = dH.vcycle_bytes(True)
     iter_bytes = vbytes + (12 * z + 4 * (n + 1) + 16 * n) + 48 * n + 16 * n + 24 * n  # + SpMV, x/r update, dot, p update
 
@@ -291,12 +294,13 @@ def run_ours(args):
                     "pcg_iterations": it_h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": f"{'csr_dict_kernel' if dict_fmt else 'csr_stream_kernel'}<{tl},EPI_JACOBI> "
+                         "kernel": f"{'csr_pattern_kernel' if pat_fmt else 'csr_dict_kernel' if dict_fmt else 'csr_stream_kernel'}<{tl},EPI_JACOBI> "
                                    "(fused Jacobi sweep, level 0)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": jac_bytes,
                          "ms_per_launch": jac_s * 1e3, "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "format": "csr-dict16 (lossless: 16-bit value/offset codes, 2 B/nnz)" if dict_fmt else "csr",
+                         "format": "csr-pattern8 (lossless: 1-byte row pattern id)" if pat_fmt else
+                                   "csr-dict16 (lossless: 16-bit value/offset codes, 2 B/nnz)" if dict_fmt else "csr",
                          "stored_bytes_per_launch": jac_stored, "stored_gbs": jac_stored / jac_s / 1e9,
                          "stored_frac": jac_stored / jac_s / 1e9 / peak,
                          "note": ("achieved counts the ALGORITHMIC CSR bytes (12 B/nnz); the kernel reads the lossless "

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(THREADS)
 // ---------------------------------------------------------------------------------------------------------
 // PATTERN kernel: csr-pattern8 (PatView, internal.cuh).  One byte per row selects the row's list of (offset, value)
 // pairs in a small table that each CTA copies into shared memory (a few KB out of L2; a warp whose rows share a
-// pattern — the common case — reads each 16-byte entry as one broadcast).  No matrix stream is left to stage: per
+// pattern — the common case — reads each entry as one broadcast).  No matrix stream is left to stage: per
 // row the kernel moves the pattern byte, the vector operands and the result, which is what bounds it.  Thread t owns
 // rows r0 + s*THREADS + t (s < RPT); all their pattern bytes and per-row operands are requested before the table copy
 // is waited for.  Escape rows (id 255) are walked from the resident CSR arrays.
