@@ -554,6 +554,14 @@ int check_handshake(sparsh_dist_s *h) {
 }
 
 // all ranks exchange equally sized byte blocks (setup only)
+int allgather_bytes_dev(const void *mine, size_t bytes, std::vector<char> &all, char *d_in, char *d_out) {
+    Comm &m = comm();
+    SP_CUDA(cudaMemcpy(d_in, mine, bytes, cudaMemcpyHostToDevice));
+    SP_NCCL(ncclAllGather(d_in, d_out, bytes, ncclChar, m.comm, ctx().stream));
+    SP_CUDA(cudaStreamSynchronize(ctx().stream));
+    SP_CUDA(cudaMemcpy(all.data(), d_out, all.size(), cudaMemcpyDeviceToHost));
+    return SPARSH_OK;
+}
 int allgather_bytes(const void *mine, size_t bytes, std::vector<char> &all) {
     Comm &m = comm();
     all.assign(bytes * (size_t)m.nranks, 0);
@@ -562,14 +570,28 @@ int allgather_bytes(const void *mine, size_t bytes, std::vector<char> &all) {
         return SPARSH_OK;
     }
     char *d_in = nullptr, *d_out = nullptr;
-    SP_CUDA(cudaMalloc(&d_in, bytes));
-    SP_CUDA(cudaMalloc(&d_out, bytes * (size_t)m.nranks));
-    SP_CUDA(cudaMemcpy(d_in, mine, bytes, cudaMemcpyHostToDevice));
-    SP_NCCL(ncclAllGather(d_in, d_out, bytes, ncclChar, m.comm, ctx().stream));
-    SP_CUDA(cudaStreamSynchronize(ctx().stream));
-    SP_CUDA(cudaMemcpy(all.data(), d_out, all.size(), cudaMemcpyDeviceToHost));
+    int rc = SPARSH_OK;
+    if (cudaMalloc(&d_in, bytes) != cudaSuccess || cudaMalloc(&d_out, bytes * (size_t)m.nranks) != cudaSuccess) {
+        set_error("out of device memory in the setup all-gather");
+        cudaGetLastError();
+        rc = SPARSH_ERR_CUDA;
+    } else {
+        rc = allgather_bytes_dev(mine, bytes, all, d_in, d_out);
+    }
     cudaFree(d_in);
     cudaFree(d_out);
+    return rc;
+}
+
+// the auxiliary stream runs the boundary strips (which feed the neighbours): highest priority, so their CTAs are
+// scheduled ahead of the interior rows that share the GPU with them
+int ensure_aux_stream(Comm &m) {
+    if (m.comm_stream) return SPARSH_OK;
+    int lo = 0, hi = 0;
+    SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SP_CUDA(cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, hi));
+    SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
+    SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
     return SPARSH_OK;
 }
 
@@ -596,16 +618,7 @@ int sparsh_dist_init(const char *id128, int nranks, int rank) {
     SP_NCCL(ncclCommInitRank(&m.comm, nranks, id, rank));
     m.nranks = nranks;
     m.rank = rank;
-    {
-        // the auxiliary stream runs the boundary strips (which feed the neighbours): highest priority, so their CTAs
-        // are scheduled ahead of the interior rows that share the GPU with them
-        int lo = 0, hi = 0;
-        SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        SP_CUDA(cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, hi));
-    }
-    SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
-    SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
-    return SPARSH_OK;
+    return ensure_aux_stream(m);
 }
 
 int sparsh_dist_finalize(void) {
@@ -653,17 +666,7 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
                                 const sparsh_params *params) {
     Comm &m = comm();
     SP_REQUIRE(m.comm != nullptr || m.nranks == 1, "sparsh_dist_init has not been called");
-    if (!m.comm_stream) {  // single-rank use without NCCL (tests): still needs the stream/event plumbing
-        {
-        // the auxiliary stream runs the boundary strips (which feed the neighbours): highest priority, so their CTAs
-        // are scheduled ahead of the interior rows that share the GPU with them
-        int lo = 0, hi = 0;
-        SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        SP_CUDA(cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, hi));
-    }
-        SP_CUDA(cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
-        SP_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
-    }
+    SP_TRY(ensure_aux_stream(m));  // single-rank use without NCCL (tests) still needs the stream/event plumbing
     if (params)
         h->prm = *params;
     else
