@@ -1,0 +1,23 @@
+#!/bin/bash
+# Developer tool (run under gpurun, one GPU): validate and time the opt-in csr-pattern8 kernel.
+#   gpurun --timeout 1500 -- 'bash tools/pattern_sweep.sh'
+# 1. opt-in parity tests  2. launch-shape sweep on the 256^3 Jacobi sweep  3. whole-solve bench with the kernel selected
+# 4. one ncu --set full capture of the pattern Jacobi kernel.  Everything lands in gpurun_out/pattern/.
+set -u
+out=gpurun_out/pattern
+mkdir -p "$out"
+SPARSH_TEST_PATTERN=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k pattern > "$out/tests.log" 2>&1
+echo "tests exit $?" | tee -a "$out/tests.log"
+grep -q "passed" "$out/tests.log" || { tail -30 "$out/tests.log"; exit 1; }
+for rpt in 2 4 8; do
+  for jb in 2 4; do
+    [ "$rpt" = 8 ] && [ "$jb" = 4 ] && continue
+    SPARSH_PATTERN=2 SPARSH_PATTERN_RPT=$rpt SPARSH_PATTERN_JB=$jb timeout 300 python tools/perf_probe.py --n 256 --reps 20 \
+      --families all 2>&1 | grep -E "^pattern|^dict128 +jacobi|^# default" | sed "s/^/rpt=$rpt jb=$jb  /" | tee -a "$out/sweep.log"
+  done
+done
+SPARSH_PATTERN=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_pattern.json" 2> "$out/bench_pattern.err"
+tail -1 "$out/bench_pattern.json"
+SPARSH_PATTERN=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:csr_pattern_kernel -s 40 -c 1 \
+  -o "$out/pattern_jacobi" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --grid 256 > "$out/ncu.log" 2>&1
+echo "ncu exit $?"
