@@ -165,9 +165,11 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
             A = host.HostMatrix.poisson3d(grid, grid, grid)
             amg = host.HostAmg(A)
             amg.save(shm)
+            amg.free()  # rank 0 drops its private copy too: one copy of the hierarchy per node, in the page cache
+            A.free()
+            A = None
         dist.barrier()
-        if rank != 0:
-            amg = host.HostAmg.load(shm)
+        amg = host.HostAmg.load(shm)
     else:
         A = host.HostMatrix.poisson3d(grid, grid, grid)
         amg = host.HostAmg(A)  # every rank builds the (sequential) host hierarchy, keeps only its part on the GPU
