@@ -330,7 +330,8 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
     }
     // ... and the per-row pattern twin when rows repeat (SPARSH_PATTERN, see pattern_mode)
     const int pmode = pattern_mode();
-    if (pmode > 0 && (A->kind == KIND_STREAM || A->kind == KIND_DICT) && nrow == ncol &&
+    // (rectangular operators qualify too: the multi-GPU local blocks are nrow x (owned + halo) with a diagonal)
+    if (pmode > 0 && (A->kind == KIND_STREAM || A->kind == KIND_DICT) &&
         build_pattern(A, h_rowptr, h_colindex, h_val, h_diag) && pmode == 1) {
         A->kind = KIND_PATTERN;
         A->threads = 128;

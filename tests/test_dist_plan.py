@@ -3,6 +3,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -19,3 +20,31 @@ def test_partition_plans_with_gloo(world, shape, coarsening):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_PLAN_OK" in out.stdout
+
+
+def test_local_blocks_keep_the_compressed_formats():
+    """The [owned | halo] relabelling of a slab partition shifts all halo columns of a block by one constant, so the
+    local blocks of a stencil hierarchy still qualify for csr-dict16 and csr-pattern8 (no escape rows)."""
+    from sparsh_amg_b200 import host
+    from sparsh_amg_b200.distributed import DistPlan
+    from sparsh_amg_b200.generators import HostCSR
+    from test_host_setup import _check_pattern_decode, _dict_encode, _pattern_encode
+
+    host.set_options(max_levels=32, print_setup=0)
+    A = host.HostMatrix.poisson3d(32, 32, 32)
+    amg = host.HostAmg(A)
+    for rank in (0, 2):
+        p = DistPlan(amg, 4, rank, tail_threshold=3000)
+        assert p.nd >= 2
+        for l in range(p.nd):
+            a = p.op(l, "A")
+            M = HostCSR(a["nrow"], a["ncol_local"] + a["nhalo"], a["rowptr"], a["colindex"], a["val"])
+            enc = _pattern_encode(M, np.ascontiguousarray(a["diag"]))
+            _check_pattern_decode(M, *enc)
+            assert 0 < enc[4] <= 27 and enc[5] == 0
+            _, dval, doff = _dict_encode(M)
+            assert 0 < len(dval) <= 3 and 0 < len(doff) <= 9
+        p.free()
+    amg.free()
+    A.free()
+    host.set_options(max_levels=6, print_setup=1)
