@@ -35,6 +35,7 @@ def load():
         lib.sparsh_host_set_option.argtypes = [C.c_char_p, C.c_double]
         for f in ("sparsh_host_matrix_poisson3d", "sparsh_host_matrix_poisson2d", "sparsh_host_matrix_diffusion27",
                   "sparsh_host_matrix_from_csr", "sparsh_host_matrix_read", "sparsh_host_matrix_read_mm",
+                  "sparsh_host_matrix_read_bin",
                   "sparsh_host_amg_setup",
                   "sparsh_host_amg_device"):
             getattr(lib, f).restype = vp
@@ -44,6 +45,8 @@ def load():
         lib.sparsh_host_matrix_from_csr.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]
         lib.sparsh_host_matrix_read.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(c_dbl_p)]
         lib.sparsh_host_matrix_read_mm.argtypes = [C.c_char_p]
+        lib.sparsh_host_matrix_read_bin.argtypes = [C.c_char_p]
+        lib.sparsh_host_matrix_write_bin.argtypes = [vp, C.c_char_p]
         lib.sparsh_host_free_array.argtypes = [c_dbl_p]
         lib.sparsh_host_matrix_prepare.argtypes = [vp]
         lib.sparsh_host_matrix_free.argtypes = [vp]
@@ -143,6 +146,18 @@ class HostMatrix:
         if not h:
             raise capi.SparshError(f"{path}: not a readable MatrixMarket coordinate file")
         return cls(h)
+
+    @classmethod
+    def read_binary(cls, path):
+        """binary CSR written by write_binary (magic SPRSHCSR; the arrays as they lie in memory)"""
+        h = load().sparsh_host_matrix_read_bin(os.fsencode(path))
+        if not h:
+            raise capi.SparshError(f"{path}: not a readable binary CSR file")
+        return cls(h)
+
+    def write_binary(self, path):
+        if self.lib.sparsh_host_matrix_write_bin(self.h, os.fsencode(path)) != 0:
+            raise capi.SparshError(f"could not write {path}")
 
     def times(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -216,6 +216,9 @@ void readcoo(char *matrixfile, char *rhsfile, sp_matrix_mg *&A, double *&b);
 void read_coo_new_format(char *matrixfile, sp_matrix_mg *&A, double *&b);
 // addition: standard MatrixMarket coordinate files (1-based, unsorted, general | symmetric | pattern); nullptr on error
 sp_matrix_mg *read_matrix_market(const char *path);
+// addition: binary CSR (magic "SPRSHCSR", version, nrow, ncol, nnz, then the three arrays); 0 on success / nullptr on error
+int write_binary_csr(const char *path, const sp_matrix_mg &A);
+sp_matrix_mg *read_binary_csr(const char *path);
 
 void AMG_Solver_CPU_baseline(sp_matrix_mg &A, double *&b, double *&x);
 void AMG_Solver_1(sp_matrix_mg &A, double *&b, double *&x);  // README name of the above

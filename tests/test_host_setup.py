@@ -335,3 +335,28 @@ def test_csr_pattern8_encoding_is_lossless(host, fixture_system):
     enc = _pattern_encode(F)
     _check_pattern_decode(F, *enc)
     assert enc[5] > 0.25 * F.nrow
+
+
+def test_binary_csr_roundtrip(host, tmp_path, fixture_system):
+    """binary CSR written and read back bit for bit; damaged files are refused"""
+    A, _ = fixture_system
+    M = host.HostMatrix.from_csr(A)
+    path = str(tmp_path / "a.csr")
+    M.write_binary(path)
+    B = host.HostMatrix.read_binary(path)
+    assert (B.nrow, B.ncol) == (A.nrow, A.ncol)
+    np.testing.assert_array_equal(B.rowptr, M.rowptr)
+    np.testing.assert_array_equal(B.colindex, M.colindex)
+    np.testing.assert_array_equal(B.val.view(np.uint64), M.val.view(np.uint64))
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"SPRSHCSR" and len(raw) == 8 + 4 * 3 + 8 + 4 * (A.nrow + 1) + 12 * A.nnz
+    for name, data in [("trunc", raw[:-16]), ("magic", b"XXXXXXXX" + raw[8:]),
+                       ("col", raw[:28 + 4 * (A.nrow + 1)] + (10 ** 9).to_bytes(4, "little") + raw[32 + 4 * (A.nrow + 1):])]:
+        bad = str(tmp_path / name)
+        open(bad, "wb").write(data)
+        with pytest.raises(Exception):
+            host.HostMatrix.read_binary(bad)
+    with pytest.raises(Exception):
+        host.HostMatrix.read_binary(str(tmp_path / "missing"))
+    B.free()
+    M.free()
