@@ -76,7 +76,8 @@ def load():
 
 def set_options(**kw):
     """threads, relax, tol, tol_mode (0 abs / 1 rel), coarse_upper, coarse_lower, max_levels, sweeps, print_setup,
-    print_solve, coarsening (0 HEM / 1 Beck), max_iter, use_graph — the run-time twins of the reference's macros."""
+    print_solve, coarsening (0 HEM / 1 Beck / 2 smoothed aggregation), max_iter, use_graph, sa_theta, sa_relax — the
+    run-time twins of the reference's macros (plus the knobs of the additions)."""
     lib = load()
     for k, v in kw.items():
         if lib.sparsh_host_set_option(k.encode(), float(v)) != 0:

@@ -197,6 +197,8 @@ void sp_matrix_mg::scale_system(double *&b) {
 // ---------------------------------------------------------------------------------------------------------
 namespace sequential {
 
+constexpr int PAT_SA_MAXROW = 512;  // distinct aggregates one fine row may touch (strong neighbours + itself)
+
 // Heavy-edge matching.  Forward sweep on even levels, backward on odd ones; a free row pairs with its free neighbour of
 // strictly largest |a_ij| (ties: first in column order; zeros never); leftovers become singletons numbered last.
 // P is n x n_coarse with a single 1.0 per row.  The greedy sweep is inherently sequential, O(nnz).
@@ -277,6 +279,139 @@ void beck_prolongator(sp_matrix_mg &A, sp_matrix_mg *&P1) {
         }
     }
     P1->sp_matrix_fill();
+}
+
+// Smoothed aggregation (Vanek, Mandel, Brezina 1996) — SURVEY §8f.2: advertised by the reference's README
+// (README.md:10,13) but absent from its sources (F2), so there is nothing to restate; this is the textbook algorithm,
+// made deterministic (natural order everywhere, no random vectors):
+//   strength   j is a strong neighbour of i  iff  j != i and |a_ij| >= theta_l * sqrt(|a_ii| |a_jj|),
+//              theta_l = sa_theta * 0.5^level
+//   pass 1     a free row whose strong neighbours are all free roots a new aggregate with them
+//   pass 2     a row still free joins the pass-1 aggregate of its strong neighbour of largest |a_ij| (ties: first)
+//   pass 3     leftovers root aggregates with their free strong neighbours (rows without any: singletons)
+//   tentative  T: one 1.0 per row (the constant near-null vector, columns left unnormalised like HEM's P)
+//   smoothing  P = (I - omega D_F^-1 A_F) T,  A_F = A with the weak off-diagonals lumped onto the diagonal,
+//              omega = sa_relax / rho,  rho = max_i sum_j |a_F,ij| / |a_F,ii|  (bound on rho(D_F^-1 A_F), = 2 for Poisson)
+void SA_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int level) {
+    const sparsh::Options &o = options();
+    const int n = A.nrow;
+    const int *rp = A.rowptr, *ci = A.colindex;
+    const double *v = A.val;
+    std::vector<double> dabs((size_t)n, 0.0);
+    for (int i = 0; i < n; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++)
+            if (ci[j] == i) {
+                dabs[i] = std::fabs(v[j]);
+                break;
+            }
+    const double theta = o.sa_theta * std::pow(0.5, level);
+    std::vector<char> strong((size_t)std::max(rp[n], 1), 0);
+#pragma omp parallel for num_threads(o.threads) schedule(static)
+    for (int i = 0; i < n; i++)
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int c = ci[j];
+            strong[j] = c != i && v[j] != 0.0 && std::fabs(v[j]) >= theta * std::sqrt(dabs[i] * dabs[c]);
+        }
+    std::vector<int> agg((size_t)n, -1);
+    int nagg = 0;
+    for (int i = 0; i < n; i++) {  // pass 1
+        if (agg[i] != -1) continue;
+        bool any = false, all_free = true;
+        for (int j = rp[i]; j < rp[i + 1] && all_free; j++)
+            if (strong[j]) {
+                any = true;
+                all_free = agg[ci[j]] == -1;
+            }
+        if (!any || !all_free) continue;
+        agg[i] = nagg;
+        for (int j = rp[i]; j < rp[i + 1]; j++)
+            if (strong[j]) agg[ci[j]] = nagg;
+        nagg++;
+    }
+    {  // pass 2 (against the snapshot left by pass 1, so the result does not depend on the sweep direction)
+        const std::vector<int> snap(agg);
+        for (int i = 0; i < n; i++) {
+            if (snap[i] != -1) continue;
+            double best = 0.0;
+            int to = -1;
+            for (int j = rp[i]; j < rp[i + 1]; j++)
+                if (strong[j] && snap[ci[j]] != -1 && std::fabs(v[j]) > best) {
+                    best = std::fabs(v[j]);
+                    to = snap[ci[j]];
+                }
+            if (to != -1) agg[i] = to;
+        }
+    }
+    for (int i = 0; i < n; i++) {  // pass 3
+        if (agg[i] != -1) continue;
+        agg[i] = nagg;
+        for (int j = rp[i]; j < rp[i + 1]; j++)
+            if (strong[j] && agg[ci[j]] == -1) agg[ci[j]] = nagg;
+        nagg++;
+    }
+    // filtered diagonal and the bound on rho(D_F^-1 A_F)
+    std::vector<double> dF((size_t)n, 0.0);
+    double rho = 0.0;
+#pragma omp parallel for num_threads(o.threads) schedule(static) reduction(max : rho)
+    for (int i = 0; i < n; i++) {
+        double d = 0.0, off = 0.0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (ci[j] == i || !strong[j])
+                d += v[j];  // weak couplings are lumped
+            else
+                off += std::fabs(v[j]);
+        }
+        dF[i] = d;
+        if (d != 0.0) rho = std::max(rho, (std::fabs(d) + off) / std::fabs(d));
+    }
+    const double omega = rho > 0.0 ? o.sa_relax / rho : 0.0;
+    // P row i = e_agg[i] - (omega / dF_i) * sum_j aF_ij e_agg[j]; entries merged per aggregate in column order of A
+    std::vector<int> cnt((size_t)n + 1, 0);
+#pragma omp parallel for num_threads(o.threads) schedule(static)
+    for (int i = 0; i < n; i++) {
+        int ids[PAT_SA_MAXROW];
+        int m = 0;
+        auto touch = [&](int a) {
+            for (int t = 0; t < m; t++)
+                if (ids[t] == a) return;
+            if (m < PAT_SA_MAXROW) ids[m++] = a;
+        };
+        touch(agg[i]);
+        if (dF[i] != 0.0)
+            for (int j = rp[i]; j < rp[i + 1]; j++)
+                if (strong[j]) touch(agg[ci[j]]);
+        cnt[i + 1] = m;
+    }
+    for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    P = new sp_matrix_mg(n, nagg, cnt[n]);
+    std::copy(cnt.begin(), cnt.end(), P->rowptr);
+#pragma omp parallel for num_threads(o.threads) schedule(static)
+    for (int i = 0; i < n; i++) {
+        int *pc = P->colindex + cnt[i];
+        double *pv = P->val + cnt[i];
+        const int cap = cnt[i + 1] - cnt[i];
+        int m = 0;
+        auto add = [&](int a, double w) {
+            for (int t = 0; t < m; t++)
+                if (pc[t] == a) {
+                    pv[t] += w;
+                    return;
+                }
+            if (m < cap) {
+                pc[m] = a;
+                pv[m] = w;
+                m++;
+            }
+        };
+        add(agg[i], 1.0);
+        if (dF[i] != 0.0) {
+            const double s = omega / dF[i];
+            add(agg[i], -s * dF[i]);  // the (filtered) diagonal term
+            for (int j = rp[i]; j < rp[i + 1]; j++)
+                if (strong[j]) add(agg[ci[j]], -s * v[j]);
+        }
+    }
+    P->sp_matrix_fill();
 }
 
 }  // namespace sequential
@@ -425,6 +560,8 @@ static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
         if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
         if (o.coarsening == sparsh::COARSEN_BECK)
             sequential::beck_prolongator(*S.Av[l], S.Pv[l]);
+        else if (o.coarsening == sparsh::COARSEN_SA)
+            sequential::SA_Prolongator(*S.Av[l], S.Pv[l], l);
         else
             sequential::HEM_Prolongator(*S.Av[l], S.Pv[l], l);
         parallel::coarsen_matrix(*S.Av[l], S.Av[l + 1], *S.Pv[l]);

@@ -64,7 +64,7 @@ struct sparsh_hierarchy_s;
 
 namespace sparsh {
 
-enum Coarsening { COARSEN_HEM = 0, COARSEN_BECK = 1 };
+enum Coarsening { COARSEN_HEM = 0, COARSEN_BECK = 1, COARSEN_SA = 2 };  // SA: smoothed aggregation (addition, F2)
 enum ToleranceMode { TOL_ABSOLUTE = 0, TOL_RELATIVE = 1 };
 
 // Run-time replacements of the reference's macros (same defaults), plus the guards the reference lacks.
@@ -84,6 +84,8 @@ struct Options {
     int max_iter = 10000;          // iteration cap (the reference's AMG and BiCGStab loops have none)
     int use_graph = 1;             // CUDA-graph the V-cycle / Krylov iteration
     int halo_mode = 1;             // multi-GPU halo exchange: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv
+    double sa_theta = 0.08;        // COARSEN_SA: strength threshold (halved per level)
+    double sa_relax = 4.0 / 3.0;   // COARSEN_SA: prolongator smoothing factor, omega = sa_relax / rho(D^-1 A)
 };
 Options &options();
 
@@ -144,6 +146,7 @@ class sp_matrix_mg : public sp_matrix {
 namespace sequential {
 void HEM_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int l1);
 void beck_prolongator(sp_matrix_mg &A, sp_matrix_mg *&P1);
+void SA_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int level);  // addition: smoothed aggregation
 }  // namespace sequential
 namespace parallel {
 void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1);  // Ac = P^T (A P), columns sorted

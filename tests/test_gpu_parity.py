@@ -224,6 +224,42 @@ def test_pattern_format_solver_history(sp, oracle, monkeypatch):
     np.testing.assert_array_equal(dx.download(), dx0.download())  # same bits as the default kernels
 
 
+@pytest.mark.skipif(os.environ.get("SPARSH_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: SPARSH_TEST_EXPERIMENTAL=1 (smoothed aggregation has not had its first GPU run)")
+def test_smoothed_aggregation_hierarchy_on_gpu(sp, oracle):
+    """a smoothed-aggregation hierarchy (general P, 30-60 nnz/row coarse operators) through the same
+    device path: V-cycle and AMG-PCG histories against the oracle running the same hierarchy."""
+    from sparsh_amg_b200 import host
+
+    host.set_options(coarsening=2, coarse_upper=500, coarse_lower=250, max_levels=32, print_setup=0)
+    try:
+        M = host.HostMatrix.poisson3d(32, 32, 32)
+        amg = host.HostAmg(M)
+        levels = []
+        for L in amg.levels():
+            A, P = L["A"], L["P"]
+            levels.append(dict(A=CSR(A.nrow, A.ncol, A.rowptr.copy(), A.colindex.copy(), A.val.copy()),
+                               diag=np.array(L["diag"]),
+                               P=None if P is None else CSR(P.nrow, P.ncol, P.rowptr.copy(), P.colindex.copy(), P.val.copy())))
+    finally:
+        host.set_options(coarsening=0, coarse_upper=4000, coarse_lower=2000, max_levels=6, print_setup=1)
+    from oracle_bindings import Hierarchy
+
+    oa = OracleAmg(hierarchy=Hierarchy(levels))
+    dH = sp.DeviceHierarchy(levels)
+    n = levels[0]["A"].nrow
+    b = np.ones(n)
+    rng = np.random.default_rng(5)
+    xr = rng.standard_normal(n)
+    db = sp.DeviceVector(data=b)
+    rel_close(dH.vcycle(db, sp.DeviceVector(data=xr), 1).download(), oa.vcycle(b, xr, 1), 1e-10)
+    _, hist_ref = oa.pcg(b, np.zeros(n), 1e-8 * np.sqrt(n))
+    it, hist, ok = dH.pcg(db, sp.DeviceVector(n).fill(0.0), 1e-8 * np.sqrt(n))
+    assert ok and abs(it - (len(hist_ref) - 1)) <= 1
+    m = min(len(hist), len(hist_ref))
+    assert_hist(hist[:m], hist_ref[:m])
+
+
 def test_edge_cases(sp, oracle):
     # 1x1
     A = CSR(1, 1, [0, 1], [0], [2.0])
