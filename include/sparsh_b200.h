@@ -202,9 +202,18 @@ int sparsh_cg(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int
               int *iters);
 int sparsh_bicgstab(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int max_iter, double *h_hist,
                     int *iters);
+/* Restarted GMRES(restart), right-preconditioned by one V-cycle (sparsh_hierarchy_pgmres) or plain (sparsh_gmres).
+ * No counterpart in the reference: README.md:13 advertises GMRES, the sources have none.  Arnoldi
+ * with classical Gram-Schmidt applied twice (fused multi-dot / multi-axpy kernels), Givens rotations on the host.
+ * restart <= 0 means 30; at most 256.  hist[0] = ||b - A x0||, hist[k] = residual-norm estimate after k inner
+ * iterations, the entry of the last iteration of each cycle replaced by the true residual norm (max_iter+1 slots). */
+int sparsh_hierarchy_pgmres(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int restart,
+                            int max_iter, double *h_hist, int *iters);
+int sparsh_gmres(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int restart, int max_iter,
+                 double *h_hist, int *iters);
 /* Host-buffer wrappers (the reference's AMG_GPU1_solver::helper, src/AMG_gpu_phases_2.cu:242-263, and the
  * cudaMemcpy prologue/epilogue of Solver_PCG_4, src/AMG_main_solvers.cu:311-312,392): H2D of b and x, solve,
- * D2H of x.  method: 0 = AMG as solver, 1 = PCG, 2 = PBiCGStab. */
+ * D2H of x.  method: 0 = AMG as solver, 1 = PCG, 2 = PBiCGStab, 3 = PGMRES(30). */
 int sparsh_hierarchy_solve_host(sparsh_hierarchy_t h, int method, const double *h_b, double *h_x, double tol,
                                 int max_iter, double *h_hist, int *iters);
 /* bytes moved by one V-cycle according to the algorithmic model of SURVEY §8d (for roofline reports) */

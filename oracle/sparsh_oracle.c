@@ -964,6 +964,113 @@ int so_pcg(so_amg *h, const double *b, double *x, double tol, int max_iter, doub
     return count;
 }
 
+/* Restarted right-preconditioned GMRES(m) with CGS2 — see sparsh_oracle.h.  Not part of the reference. */
+int so_gmres(so_amg *h, int n, const int *rp, const int *ci, const double *v, const double *b, double *x, double tol,
+             int restart, int max_iter, double *hist) {
+    if (h) {
+        n = h->lev[0].n;
+        rp = h->lev[0].rp;
+        ci = h->lev[0].ci;
+        v = h->lev[0].v;
+    }
+    const int m = restart > 0 ? restart : 30;
+    size_t bytes = sizeof(double) * (size_t)n;
+    double *V = (double *)xmalloc(bytes * (size_t)(m + 1));
+    double *z = (double *)xmalloc(bytes), *w = (double *)xmalloc(bytes), *u = (double *)xmalloc(bytes);
+    double *H = (double *)xcalloc((size_t)(m + 1) * (size_t)m, sizeof(double)); /* column j at H + j*(m+1) */
+    double *cs = (double *)xmalloc(sizeof(double) * (size_t)m), *sn = (double *)xmalloc(sizeof(double) * (size_t)m);
+    double *g = (double *)xmalloc(sizeof(double) * (size_t)(m + 1)), *y = (double *)xmalloc(sizeof(double) * (size_t)m);
+    double *hc = (double *)xmalloc(sizeof(double) * (size_t)(m + 1));
+    so_store_residual(n, rp, ci, v, b, x, w);
+    double beta = so_nrm2(n, w);
+    if (hist) hist[0] = beta;
+    int it = 0;
+    while (beta > tol && it < max_iter) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int i = 0; i < n; i++) V[i] = w[i] / beta;
+        g[0] = beta;
+        int j = 0;
+        double est = beta;
+        while (j < m && it < max_iter) {
+            double *vj = V + (size_t)j * (size_t)n, *vn = V + (size_t)(j + 1) * (size_t)n, *Hj = H + (size_t)j * (size_t)(m + 1);
+            if (h) {
+                memset(z, 0, bytes);
+                so_amg_vcycle(h, vj, z, 1);
+                so_spmv(n, rp, ci, v, z, w);
+            } else {
+                so_spmv(n, rp, ci, v, vj, w);
+            }
+            for (int pass = 0; pass < 2; pass++) { /* classical Gram-Schmidt, twice */
+                for (int i = 0; i <= j; i++) hc[i] = so_dot(n, V + (size_t)i * (size_t)n, w);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+                for (int r = 0; r < n; r++) {
+                    double t = w[r];
+                    for (int i = 0; i <= j; i++) t -= hc[i] * V[(size_t)i * (size_t)n + (size_t)r];
+                    w[r] = t;
+                }
+                for (int i = 0; i <= j; i++) Hj[i] = pass == 0 ? hc[i] : Hj[i] + hc[i];
+            }
+            double hn = so_nrm2(n, w);
+            Hj[j + 1] = hn;
+            if (hn > 0.0) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+                for (int r = 0; r < n; r++) vn[r] = w[r] / hn;
+            }
+            for (int i = 0; i < j; i++) { /* earlier rotations */
+                double t = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
+                Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1];
+                Hj[i] = t;
+            }
+            double den = sqrt(Hj[j] * Hj[j] + Hj[j + 1] * Hj[j + 1]);
+            cs[j] = den > 0.0 ? Hj[j] / den : 1.0;
+            sn[j] = den > 0.0 ? Hj[j + 1] / den : 0.0;
+            Hj[j] = den;
+            Hj[j + 1] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            est = fabs(g[j + 1]);
+            j++;
+            it++;
+            if (hist) hist[it] = est;
+            if (est <= tol || hn == 0.0) break;
+        }
+        for (int i = j - 1; i >= 0; i--) { /* back substitution */
+            double t = g[i];
+            for (int k = i + 1; k < j; k++) t -= H[(size_t)k * (size_t)(m + 1) + (size_t)i] * y[k];
+            y[i] = t / H[(size_t)i * (size_t)(m + 1) + (size_t)i];
+        }
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int r = 0; r < n; r++) {
+            double t = 0.0;
+            for (int i = 0; i < j; i++) t += y[i] * V[(size_t)i * (size_t)n + (size_t)r];
+            u[r] = t;
+        }
+        if (h) {
+            memset(z, 0, bytes);
+            so_amg_vcycle(h, u, z, 1);
+        } else {
+            memcpy(z, u, bytes);
+        }
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int r = 0; r < n; r++) x[r] += z[r];
+        so_store_residual(n, rp, ci, v, b, x, w);
+        beta = so_nrm2(n, w);
+        if (hist) hist[it] = beta;
+        if (j == 0) break;
+    }
+    free(V);
+    free(z);
+    free(w);
+    free(u);
+    free(H);
+    free(cs);
+    free(sn);
+    free(g);
+    free(y);
+    free(hc);
+    return it;
+}
+
 /* src/AMG_main_solvers.cpp:358-458 */
 int so_pbicgstab(so_amg *h, const double *b, double *x, double tol, int max_iter, double *hist) {
     so_level *A = &h->lev[0];

@@ -108,6 +108,15 @@ int so_cg(int n, const int *rp, const int *ci, const double *v, const double *b,
 int so_bicgstab(int n, const int *rp, const int *ci, const double *v, const double *b, double *x, double tol,
                 int max_iter, double *hist);
 
+/* Restarted GMRES(m), right-preconditioned by one V-cycle of h (h == NULL: unpreconditioned, then the matrix is
+ * (n, rp, ci, v)).  NOT in the reference (advertised by README.md:13, no code) — this states the algorithm
+ * the CUDA path implements so that the two can be compared: Arnoldi with classical Gram-Schmidt applied twice (CGS2),
+ * Givens rotations, x += M^-1 (V y) at the end of each cycle, true residual recomputed at every restart.
+ * hist[0] = ||b - A x0||, hist[k] = Givens estimate of the residual norm after k inner iterations, except that the
+ * entry of the last iteration of a cycle is overwritten by the true residual norm.  Returns inner iterations done. */
+int so_gmres(so_amg *h, int n, const int *rp, const int *ci, const double *v, const double *b, double *x, double tol,
+             int restart, int max_iter, double *hist);
+
 /* AMG_solver_setup_SOR (src/AMG_phases.cpp:94-147): every level colour-permuted (color_matrix_and_reorder), P columns
  * re-labelled by the coarse permutation (reorder_prolongator, src/AMG_cycle_utilities.cpp:149-188). */
 so_amg *so_amg_setup_sor(int n, const int *rp, const int *ci, const double *v, int max_levels, int limit_upper,

@@ -88,6 +88,8 @@ SIGNATURES = {
     "sparsh_hierarchy_pbicgstab": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
     "sparsh_cg": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
     "sparsh_bicgstab": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
+    "sparsh_hierarchy_pgmres": (_i, [_vp, _vp, _vp, _d, _i, _i, c_dbl_p, c_int_p]),
+    "sparsh_gmres": (_i, [_vp, _vp, _vp, _d, _i, _i, c_dbl_p, c_int_p]),
     "sparsh_hierarchy_solve_host": (_i, [_vp, _i, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
     "sparsh_hierarchy_vcycle_bytes": (_d, [_vp, _i]),
     # multi-GPU

@@ -121,6 +121,51 @@ __global__ void __launch_bounds__(BT)
     reduce_finalize<2>(v, partials, ticket, out);
 }
 
+// ---- GMRES(m) building blocks (not in the reference; arithmetic order = oracle so_gmres) ------------
+// up to 4 dots of w against consecutive basis vectors in ONE pass over w: out[q] = V_q . w
+__global__ void __launch_bounds__(BT)
+    mdot4_kernel(size_t n, const double *__restrict__ V, size_t ld, int cnt, const double *__restrict__ w, double *partials,
+                 unsigned int *ticket, double *out) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < n; i += (size_t)gridDim.x * BT) {
+        const double wi = w[i];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (q < cnt) v[q] = __dadd_rn(v[q], __dmul_rn(V[(size_t)q * ld + i], wi));
+    }
+    reduce_finalize<4>(v, partials, ticket, out);
+}
+// w -= sum_q h[q] V_q  (q ascending; h in device memory)
+__global__ void __launch_bounds__(BT)
+    maxpy_sub_kernel(size_t n, const double *__restrict__ V, size_t ld, int k, const double *__restrict__ h, double *w) {
+    extern __shared__ double sh[];
+    for (int q = threadIdx.x; q < k; q += BT) sh[q] = h[q];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < n; i += (size_t)gridDim.x * BT) {
+        double t = w[i];
+        for (int q = 0; q < k; q++) t = __dsub_rn(t, __dmul_rn(sh[q], V[(size_t)q * ld + i]));
+        w[i] = t;
+    }
+}
+// out = sum_q y[q] V_q  (q ascending, from 0.0)
+__global__ void __launch_bounds__(BT)
+    lincomb_kernel(size_t n, const double *__restrict__ V, size_t ld, int k, const double *__restrict__ y, double *out) {
+    extern __shared__ double sh[];
+    for (int q = threadIdx.x; q < k; q += BT) sh[q] = y[q];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < n; i += (size_t)gridDim.x * BT) {
+        double t = 0.0;
+        for (int q = 0; q < k; q++) t = __dadd_rn(t, __dmul_rn(sh[q], V[(size_t)q * ld + i]));
+        out[i] = t;
+    }
+}
+// out = in / sqrt(*nrm2)
+__global__ void __launch_bounds__(BT)
+    scale_inv_sqrt_kernel(size_t n, const double *__restrict__ in, const double *nrm2, double *out) {
+    const double d = sqrt(*nrm2);
+    for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < n; i += (size_t)gridDim.x * BT) out[i] = __ddiv_rn(in[i], d);
+}
+
 // ---- PCG (src/AMG_main_solvers.cpp:140-150) -----------------------------------------------------------------
 // alpha = rz/pAp (:142); x += alpha p (:144); r += (-alpha) Ap (:145); rr = r.r (for :152)
 __global__ void __launch_bounds__(BT)
@@ -231,6 +276,28 @@ int k_dot(size_t n, const double *x, const double *y, double *d_out) {
 int k_dot2(size_t n, const double *a, const double *b, const double *cc, double *d_out2) {
     Context &c = ctx();
     dot2_kernel<<<stream_grid(n), BT, 0, c.stream>>>(n, a, b, cc, c.partials, c.ticket, d_out2);
+    LAUNCH_CHECK();
+}
+int k_mdot(size_t n, const double *V, size_t ld, int k, const double *w, double *d_out) {
+    Context &c = ctx();
+    for (int j0 = 0; j0 < k; j0 += 4) {  // d_out must have room for k rounded up to a multiple of 4
+        mdot4_kernel<<<stream_grid(n), BT, 0, c.stream>>>(n, V + (size_t)j0 * ld, ld, k - j0 < 4 ? k - j0 : 4, w, c.partials,
+                                                          c.ticket, d_out + j0);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+    }
+    return SPARSH_OK;
+}
+int k_maxpy_sub(size_t n, const double *V, size_t ld, int k, const double *d_h, double *w) {
+    maxpy_sub_kernel<<<stream_grid(n), BT, sizeof(double) * (size_t)k, ctx().stream>>>(n, V, ld, k, d_h, w);
+    LAUNCH_CHECK();
+}
+int k_lincomb(size_t n, const double *V, size_t ld, int k, const double *d_y, double *out) {
+    lincomb_kernel<<<stream_grid(n), BT, sizeof(double) * (size_t)k, ctx().stream>>>(n, V, ld, k, d_y, out);
+    LAUNCH_CHECK();
+}
+int k_scale_inv_sqrt(size_t n, const double *in, const double *d_nrm2, double *out) {
+    scale_inv_sqrt_kernel<<<stream_grid(n), BT, 0, ctx().stream>>>(n, in, d_nrm2, out);
     LAUNCH_CHECK();
 }
 int k_pcg_update_xr(size_t n, const double *p, const double *Ap, double *x, double *r, const double *rz,

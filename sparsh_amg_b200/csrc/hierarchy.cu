@@ -183,6 +183,9 @@ int sparsh_hierarchy_destroy(sparsh_hierarchy_t h) {
     cudaFreeHost(h->h_sc);
     cudaFree(h->hb);
     cudaFree(h->hx);
+    cudaFree(h->gm_V);
+    cudaFree(h->gm_d);
+    cudaFreeHost(h->gm_h);
     delete h;
     return SPARSH_OK;
 }

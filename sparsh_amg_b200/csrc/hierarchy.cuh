@@ -38,6 +38,9 @@ struct sparsh_hierarchy_s {
     double *d_sc = nullptr;  // 16 doubles
     double *h_sc = nullptr;  // pinned mirror
     double *hb = nullptr, *hx = nullptr;  // device staging for the host-buffer wrappers
+    // GMRES(m) workspace (allocated on first use): basis, device scalars [h | h2 | norm | y], pinned mirror
+    double *gm_V = nullptr, *gm_d = nullptr, *gm_h = nullptr;
+    int gm_m = 0;
     std::vector<sparsh::GraphEntry> graphs;
 };
 

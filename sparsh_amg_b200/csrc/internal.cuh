@@ -211,6 +211,12 @@ int k_bicg_xr(size_t n, double *x, const double *ph, const double *sh, const dou
               double *out2);
 int k_bicg_p(size_t n, const double *r, double *p, const double *Ap, const double *sc);
 int k_dot2(size_t n, const double *a, const double *b, const double *c, double *d_out2);  // out[0]=a.b out[1]=a.c
+// GMRES(m): V holds basis vectors ld apart.  d_out[q] = V_q.w for q < k (d_out needs k rounded up to 4 slots);
+// w -= sum h[q] V_q;  out = sum y[q] V_q;  out = in / sqrt(*d_nrm2)
+int k_mdot(size_t n, const double *V, size_t ld, int k, const double *w, double *d_out);
+int k_maxpy_sub(size_t n, const double *V, size_t ld, int k, const double *d_h, double *w);
+int k_lincomb(size_t n, const double *V, size_t ld, int k, const double *d_y, double *out);
+int k_scale_inv_sqrt(size_t n, const double *in, const double *d_nrm2, double *out);
 
 // ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------
 struct CoarseInverse {

@@ -14,6 +14,7 @@
 //    (src/AMG_main_solvers.cpp:146) — the fill and the first Jacobi matrix pass disappear;
 //  * one iteration = one CUDA graph launch.
 #include <cmath>
+#include <vector>
 
 #include "hierarchy.cuh"
 
@@ -55,6 +56,9 @@ struct TmpHier {
         for (int i = 0; i < 8; i++) cudaFree(h.kv[i]);
         cudaFree(h.d_sc);
         cudaFreeHost(h.h_sc);
+        cudaFree(h.gm_V);
+        cudaFree(h.gm_d);
+        cudaFreeHost(h.gm_h);
         h.lev.clear();
     }
 };
@@ -185,6 +189,120 @@ int bicg_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, d
     return res <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
 }
 
+// ---- GMRES(m) ----------------------------------------------------------------------------------------------
+// Not in the reference (README.md:13 advertises it, no code) — SURVEY §8f.2.  Restarted GMRES, right-
+// preconditioned by one V-cycle (precond) or plain; the arithmetic is the oracle's so_gmres: Arnoldi with classical
+// Gram-Schmidt applied twice — two fused multi-dot passes (4 dots per sweep over w) and two fused multi-axpy passes
+// instead of 2(j+1) separate dot/axpy pairs —, Givens rotations on the host from ONE device-to-host copy of the j+2
+// scalars per inner iteration, x += M^-1 (V y) per cycle, true residual at every restart.  The V-cycle replays the same
+// CUDA graph as PCG's (the basis vector is staged through a fixed input vector).
+int gmres_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, double tol, int restart, int max_iter,
+               double *hist, int *iters_out) {
+    sparsh_matrix_s *A = h->lev[0].A;
+    const size_t n = (size_t)A->nrow;
+    const size_t ld = (n + 3) & ~(size_t)3;  // basis vectors 32-byte aligned
+    const int m = restart > 0 ? restart : 30;
+    SP_REQUIRE(m <= 256, "GMRES restart length above 256");
+    Context &c = ctx();
+    SP_TRY(krylov_workspace(h, 3));
+    double *vin = h->kv[0], *z = h->kv[1], *w = h->kv[2];
+    const int HS = ((m + 1) + 3) & ~3;  // slots per coefficient vector (multi-dot writes whole groups of 4)
+    const int NS = 2 * HS + 4 + m;      // [h | h2 | norm (+3 pad) | y]
+    if (h->gm_m < m) {
+        SP_CUDA(cudaStreamSynchronize(c.stream));
+        cudaFree(h->gm_V);
+        cudaFree(h->gm_d);
+        cudaFreeHost(h->gm_h);
+        h->gm_V = h->gm_d = h->gm_h = nullptr;
+        h->gm_m = 0;
+        SP_CUDA(cudaMalloc(&h->gm_V, sizeof(double) * ld * (size_t)(m + 1)));
+        SP_CUDA(cudaMalloc(&h->gm_d, sizeof(double) * (size_t)NS));
+        SP_CUDA(cudaMallocHost(&h->gm_h, sizeof(double) * (size_t)NS));
+        h->gm_m = m;
+    }
+    double *V = h->gm_V, *d_h = h->gm_d, *d_h2 = h->gm_d + HS, *d_nrm = h->gm_d + 2 * HS, *d_y = h->gm_d + 2 * HS + 4;
+    double *hh = h->gm_h;
+    auto residual_norm2 = [&]() -> int {  // w = b - A x, *d_nrm = w.w, mirrored to the host
+        EpiArgs a;
+        a.b = b;
+        SP_TRY(launch_csr(A, EPI_RESID, x, w, a, 0, A->nrow));
+        SP_TRY(k_dot(n, w, w, d_nrm));
+        SP_CUDA(cudaMemcpyAsync(hh + 2 * HS, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        return sync_stream();
+    };
+    auto precondition = [&](const double *in, double *out) -> int {  // out = M^-1 in
+        SP_CUDA(cudaMemcpyAsync(vin, in, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+        return run_graphed(h, vin, out, 1, [&]() { return enqueue_vcycle(h, vin, out, true); });
+    };
+    std::vector<double> H((size_t)(m + 1) * (size_t)m, 0.0), cs(m), sn(m), g(m + 1), y(m);
+    SP_TRY(residual_norm2());
+    double beta = std::sqrt(hh[2 * HS]);
+    if (hist) hist[0] = beta;
+    int it = 0;
+    while (beta > tol && it < max_iter && std::isfinite(beta)) {
+        SP_TRY(k_scale_inv_sqrt(n, w, d_nrm, V));
+        g[0] = beta;
+        int j = 0;
+        while (j < m && it < max_iter) {
+            double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld, *Hj = H.data() + (size_t)j * (size_t)(m + 1);
+            if (precond) {
+                SP_TRY(precondition(vj, z));
+                SP_TRY(launch_csr(A, EPI_SPMV, z, w, EpiArgs(), 0, A->nrow));
+            } else {
+                SP_TRY(launch_csr(A, EPI_SPMV, vj, w, EpiArgs(), 0, A->nrow));
+            }
+            SP_TRY(k_mdot(n, V, ld, j + 1, w, d_h));
+            SP_TRY(k_maxpy_sub(n, V, ld, j + 1, d_h, w));
+            SP_TRY(k_mdot(n, V, ld, j + 1, w, d_h2));
+            SP_TRY(k_maxpy_sub(n, V, ld, j + 1, d_h2, w));
+            SP_TRY(k_dot(n, w, w, d_nrm));
+            SP_TRY(k_scale_inv_sqrt(n, w, d_nrm, vn));
+            SP_CUDA(cudaMemcpyAsync(hh, h->gm_d, sizeof(double) * (size_t)(2 * HS + 1), cudaMemcpyDeviceToHost, c.stream));
+            SP_TRY(sync_stream());
+            for (int i = 0; i <= j; i++) Hj[i] = hh[i] + hh[HS + i];
+            const double hn = std::sqrt(hh[2 * HS]);
+            Hj[j + 1] = hn;
+            for (int i = 0; i < j; i++) {  // earlier rotations
+                const double t = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
+                Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1];
+                Hj[i] = t;
+            }
+            const double den = std::sqrt(Hj[j] * Hj[j] + Hj[j + 1] * Hj[j + 1]);
+            cs[j] = den > 0.0 ? Hj[j] / den : 1.0;
+            sn[j] = den > 0.0 ? Hj[j + 1] / den : 0.0;
+            Hj[j] = den;
+            Hj[j + 1] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            const double est = std::fabs(g[j + 1]);
+            j++;
+            it++;
+            if (hist) hist[it] = est;
+            if (est <= tol || hn == 0.0 || !std::isfinite(est)) break;
+        }
+        for (int i = j - 1; i >= 0; i--) {  // back substitution
+            double t = g[i];
+            for (int k = i + 1; k < j; k++) t -= H[(size_t)k * (size_t)(m + 1) + (size_t)i] * y[k];
+            y[i] = t / H[(size_t)i * (size_t)(m + 1) + (size_t)i];
+        }
+        if (j == 0) break;
+        for (int i = 0; i < j; i++) hh[2 * HS + 4 + i] = y[i];
+        SP_CUDA(cudaMemcpyAsync(d_y, hh + 2 * HS + 4, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, c.stream));
+        SP_TRY(k_lincomb(n, V, ld, j, d_y, w));
+        if (precond) {
+            SP_TRY(precondition(w, z));
+            SP_TRY(k_axpy(n, 1.0, z, x));
+        } else {
+            SP_TRY(k_axpy(n, 1.0, w, x));
+        }
+        SP_TRY(residual_norm2());
+        beta = std::sqrt(hh[2 * HS]);
+        if (hist) hist[it] = beta;
+    }
+    if (iters_out) *iters_out = it;
+    return beta <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
+}
+
 }  // namespace
 
 extern "C" {
@@ -199,6 +317,20 @@ int sparsh_hierarchy_pbicgstab(sparsh_hierarchy_t h, const double *d_b, double *
                                double *h_hist, int *iters) {
     SP_REQUIRE(h != nullptr, "hierarchy is NULL");
     return bicg_impl(h, true, d_b, d_x, tol, max_iter, h_hist, iters);
+}
+
+int sparsh_hierarchy_pgmres(sparsh_hierarchy_t h, const double *d_b, double *d_x, double tol, int restart,
+                            int max_iter, double *h_hist, int *iters) {
+    SP_REQUIRE(h != nullptr, "hierarchy is NULL");
+    return gmres_impl(h, true, d_b, d_x, tol, restart, max_iter, h_hist, iters);
+}
+
+int sparsh_gmres(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int restart, int max_iter,
+                 double *h_hist, int *iters) {
+    SP_REQUIRE(A != nullptr && A->nrow == A->ncol, "gmres needs a square matrix");
+    TmpHier t(A);
+    SP_TRY(t.init());
+    return gmres_impl(&t.h, false, d_b, d_x, tol, restart, max_iter, h_hist, iters);
 }
 
 int sparsh_cg(sparsh_matrix_t A, const double *d_b, double *d_x, double tol, int max_iter, double *h_hist, int *iters) {
@@ -233,6 +365,8 @@ int sparsh_hierarchy_solve_host(sparsh_hierarchy_t h, int method, const double *
         rc = sparsh_hierarchy_pcg(h, h->hb, h->hx, tol, max_iter, h_hist, iters);
     else if (method == 2)
         rc = sparsh_hierarchy_pbicgstab(h, h->hb, h->hx, tol, max_iter, h_hist, iters);
+    else if (method == 3)
+        rc = sparsh_hierarchy_pgmres(h, h->hb, h->hx, tol, 30, max_iter, h_hist, iters);
     else {
         set_error("unknown method");
         return SPARSH_ERR_INVALID;

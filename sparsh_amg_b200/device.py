@@ -160,6 +160,10 @@ class DeviceMatrix:
     def bicgstab(self, b, x, tol, max_iter=10000):
         return _krylov(self.lib.sparsh_bicgstab, self.h, b, x, tol, max_iter)
 
+    def gmres(self, b, x, tol, restart=30, max_iter=10000):
+        """unpreconditioned GMRES(restart) (addition: SURVEY §8f.2)"""
+        return _gmres(self.lib.sparsh_gmres, self.h, b, x, tol, restart, max_iter)
+
     def free(self):
         if self.owned and getattr(self, "h", None):
             self.lib.sparsh_matrix_destroy(self.h)
@@ -176,6 +180,14 @@ def _krylov(fn, handle, b, x, tol, max_iter):
     hist = np.zeros(max_iter + 1)
     it = C.c_int()
     rc = check(fn(handle, b.ptr, x.ptr, float(tol), int(max_iter), dp(hist), C.byref(it)), allow_not_converged=True)
+    return it.value, hist[: it.value + 1], rc == capi.SPARSH_OK
+
+
+def _gmres(fn, handle, b, x, tol, restart, max_iter):
+    hist = np.zeros(max_iter + 1)
+    it = C.c_int()
+    rc = check(fn(handle, b.ptr, x.ptr, float(tol), int(restart), int(max_iter), dp(hist), C.byref(it)),
+               allow_not_converged=True)
     return it.value, hist[: it.value + 1], rc == capi.SPARSH_OK
 
 
@@ -269,6 +281,10 @@ class DeviceHierarchy:
 
     def pbicgstab(self, b, x, tol, max_iter=500):
         return _krylov(self.lib.sparsh_hierarchy_pbicgstab, self.h, b, x, tol, max_iter)
+
+    def pgmres(self, b, x, tol, restart=30, max_iter=500):
+        """V-cycle-preconditioned GMRES(restart) (addition: SURVEY §8f.2)"""
+        return _gmres(self.lib.sparsh_hierarchy_pgmres, self.h, b, x, tol, restart, max_iter)
 
     def solve_host(self, method, b_host, x_host, tol, max_iter=500):
         """method: 'amg' | 'pcg' | 'pbicgstab'; b_host/x_host are numpy arrays (x in/out)"""

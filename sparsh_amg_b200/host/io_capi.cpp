@@ -316,6 +316,7 @@ int sparsh_host_set_option(const char *name, double value) {
     else if (s == "max_iter") o.max_iter = (int)value;
     else if (s == "use_graph") o.use_graph = (int)value;
     else if (s == "halo_mode") o.halo_mode = (int)value;
+    else if (s == "gmres_restart") o.gmres_restart = (int)value;
     else if (s == "sa_theta") o.sa_theta = value;
     else if (s == "sa_relax") o.sa_relax = value;
     else return -1;
@@ -451,6 +452,8 @@ int sparsh_host_call(const char *name, void *Av, const double *b, double *x) {
                                   {"Solver_PBiCG_2", Solver_PBiCG_2},
                                   {"Solver_PBiCG_3", Solver_PBiCG_3},
                                   {"Solver_PBiCG_4", Solver_PBiCG_4},
+                                  {"Solver_GMRES_1", Solver_GMRES_1},
+                                  {"Solver_PGMRES_1", Solver_PGMRES_1},
                                   {"coarsening_2", coarsening_2}};
     for (const Entry &e : table)
         if (s == e.n) {

@@ -218,7 +218,7 @@ sp_matrix_gpu::~sp_matrix_gpu() {
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-enum Method { M_AMG = 0, M_PCG = 1, M_PBICG = 2 };
+enum Method { M_AMG = 0, M_PCG = 1, M_PBICG = 2, M_PGMRES = 3 };
 
 // setup + upload + solve with host b/x, timing printed like the reference's wrappers
 void amg_driver(sp_matrix_mg &A, double *b, double *x, Method m, bool sor, const char *label) {
@@ -258,7 +258,9 @@ void amg_driver(sp_matrix_mg &A, double *b, double *x, Method m, bool sor, const
     delete S;
 }
 
-void krylov_driver(sp_matrix_mg &A, double *b, double *x, bool cg, const char *label) {
+enum Plain { K_CG = 0, K_BICG = 1, K_GMRES = 2 };
+void krylov_driver(sp_matrix_mg &A, double *b, double *x, Plain which, const char *label) {
+    const bool cg = which == K_CG;
     const sparsh::Options &o = options();
     const int n = A.nrow;
     sparsh_matrix_t dA = nullptr;
@@ -273,8 +275,9 @@ void krylov_driver(sp_matrix_mg &A, double *b, double *x, bool cg, const char *l
     std::vector<double> hist((size_t)o.max_iter + 2, 0.0);
     int it = 0;
     const double tol = effective_tol(b, n);
-    int rc = cg ? sparsh_cg(dA, db, dx, tol, o.max_iter, hist.data(), &it)
-                : sparsh_bicgstab(dA, db, dx, tol, o.max_iter, hist.data(), &it);
+    int rc = cg                 ? sparsh_cg(dA, db, dx, tol, o.max_iter, hist.data(), &it)
+             : which == K_BICG ? sparsh_bicgstab(dA, db, dx, tol, o.max_iter, hist.data(), &it)
+                               : sparsh_gmres(dA, db, dx, tol, o.gmres_restart, o.max_iter, hist.data(), &it);
     if (rc != SPARSH_OK && rc != SPARSH_ERR_NOT_CONVERGED) die(label, rc);
     CK(sparsh_memcpy_d2h(x, dx, sizeof(double) * (size_t)n));
     record(rc, it, hist, omp_get_wtime() - t0, label, cg ? 1 : 0);
@@ -293,9 +296,12 @@ void AMG_Solver_2(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x,
 void AMG_Solver_CPU_GPU_CI(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x, M_AMG, false, "Time AMG Hybrid AMG 1"); }
 void AMG_Solver_CPU_GPU_MI(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x, M_AMG, false, "Time AMG Hybrid AMG 2"); }
 
-void Solver_CG_1(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, true, "CG"); }
-void Solver_CG_2(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, true, "CG"); }
-void Solver_BiCG_1(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, false, "BiCGStab"); }
+void Solver_CG_1(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, K_CG, "CG"); }
+void Solver_CG_2(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, K_CG, "CG"); }
+void Solver_BiCG_1(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, K_BICG, "BiCGStab"); }
+// additions (the reference's README advertises GMRES, its sources have none: SURVEY F3, §8f.2)
+void Solver_GMRES_1(sp_matrix_mg &A, double *&b, double *&x) { krylov_driver(A, b, x, K_GMRES, "GMRES"); }
+void Solver_PGMRES_1(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x, M_PGMRES, false, "PGMRES"); }
 
 void Solver_PCG_1(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x, M_PCG, false, "PCG"); }
 void Solver_PCG_2(sp_matrix_mg &A, double *&b, double *&x) { amg_driver(A, b, x, M_PCG, false, "PCG-2"); }

@@ -84,6 +84,7 @@ struct Options {
     int max_iter = 10000;          // iteration cap (the reference's AMG and BiCGStab loops have none)
     int use_graph = 1;             // CUDA-graph the V-cycle / Krylov iteration
     int halo_mode = 1;             // multi-GPU halo exchange: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv
+    int gmres_restart = 30;        // Solver_GMRES_1 / Solver_PGMRES_1 (used by sparsh_gmres; the host-buffer path uses 30)
     double sa_theta = 0.08;        // COARSEN_SA: strength threshold (halved per level)
     double sa_relax = 4.0 / 3.0;   // COARSEN_SA: prolongator smoothing factor, omega = sa_relax / rho(D^-1 A)
 };
@@ -240,5 +241,8 @@ void Solver_PBiCG_2(sp_matrix_mg &A, double *&b, double *&x);
 void Solver_PBiCG_3(sp_matrix_mg &A, double *&b, double *&x);
 void Solver_PBiCG_4(sp_matrix_mg &A, double *&b, double *&x);
 void coarsening_2(sp_matrix_mg &A, double *&b, double *&x);
+// additions: restarted GMRES(options().gmres_restart), plain and V-cycle-preconditioned
+void Solver_GMRES_1(sp_matrix_mg &A, double *&b, double *&x);
+void Solver_PGMRES_1(sp_matrix_mg &A, double *&b, double *&x);
 
 #endif  // SPARSH_AMG_HPP_

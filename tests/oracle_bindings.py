@@ -80,6 +80,8 @@ class Oracle:
         lib.so_free.argtypes = [C.c_void_p]
         lib.so_amg_setup.restype = C.c_void_p
         lib.so_amg_from_levels.restype = C.c_void_p
+        lib.so_gmres.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_double, C.c_int,
+                                 C.c_int, c_dbl_p]
         lib.so_amg_setup_sor.restype = C.c_void_p
         lib.so_amg_solve_sor.argtypes = [C.c_void_p, c_dbl_p, c_dbl_p, C.c_double, C.c_int, c_dbl_p]
         for f in ("so_amg_free", "so_amg_nlevels"):
@@ -107,6 +109,14 @@ class Oracle:
         y = np.empty(A.nrow)
         self.lib.so_spmv(A.nrow, ip(A.rowptr), ip(A.colindex), dp(A.val), dp(x), dp(y))
         return y
+
+    def gmres(self, A, b, x, tol, restart=30, max_iter=500):
+        """unpreconditioned GMRES(restart): (x, hist)"""
+        x = x.copy()
+        hist = np.zeros(max_iter + 1)
+        k = self.lib.so_gmres(None, A.nrow, ip(A.rowptr), ip(A.colindex), dp(A.val), dp(b), dp(x), tol, restart, max_iter,
+                              dp(hist))
+        return x, hist[: k + 1]
 
     def jacobi(self, A, diag, b, x, omega, iteration):
         x = x.copy()
@@ -301,6 +311,12 @@ class OracleAmg:
         x = x.copy()
         hist = np.zeros(max_cycles + 1)
         k = self.o.lib.so_amg_solve_sor(self.h, dp(b), dp(x), tol, max_cycles, dp(hist))
+        return x, hist[: k + 1]
+
+    def pgmres(self, b, x, tol, restart=30, max_iter=500):
+        x = x.copy()
+        hist = np.zeros(max_iter + 1)
+        k = self.o.lib.so_gmres(self.h, 0, None, None, None, dp(b), dp(x), tol, restart, max_iter, dp(hist))
         return x, hist[: k + 1]
 
     def pcg(self, b, x, tol, max_iter=500):

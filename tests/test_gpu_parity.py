@@ -260,6 +260,42 @@ def test_smoothed_aggregation_hierarchy_on_gpu(sp, oracle):
     assert_hist(hist[:m], hist_ref[:m])
 
 
+@pytest.mark.skipif(os.environ.get("SPARSH_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: SPARSH_TEST_EXPERIMENTAL=1 (GMRES has not had its first GPU run)")
+def test_gmres_matches_the_oracle_statement(sp, oracle, fixture_system):
+    """restarted GMRES (CGS2 + Givens) on the device against the oracle's statement of the same algorithm:
+    plain on a nonsymmetric matrix (full and restarted), V-cycle-preconditioned on the bundled system."""
+    import scipy.sparse as sps
+
+    rng = np.random.default_rng(11)
+    n = 3000
+    S = (sps.diags([-1.3, 2.6, -0.7], [-1, 0, 1], shape=(n, n)) + sps.random(n, n, density=0.001, random_state=3) * 0.2).tocsr()
+    S.sort_indices()
+    A = CSR(n, n, S.indptr, S.indices, S.data)
+    b = rng.standard_normal(n)
+    tol = 1e-9 * np.linalg.norm(b)
+    dA = sp.DeviceMatrix.from_csr(A)
+    db = sp.DeviceVector(data=b)
+    for restart in (200, 10):
+        x_ref, h_ref = oracle.gmres(A, b, np.zeros(n), tol, restart=restart, max_iter=2000)
+        dx = sp.DeviceVector(n).fill(0.0)
+        it, hist, ok = dA.gmres(db, dx, tol, restart=restart, max_iter=2000)
+        assert ok and abs(it - (len(h_ref) - 1)) <= 1
+        m = min(len(hist), len(h_ref))
+        np.testing.assert_allclose(hist[:m], h_ref[:m], rtol=1e-7, atol=1e-13 * h_ref[0])
+        assert np.linalg.norm(b - S @ dx.download()) <= tol * (1 + 1e-6)
+    F, fb = fixture_system
+    amg = OracleAmg(F)
+    _, hp_ref = amg.pgmres(fb, np.zeros(F.nrow), 1e-8, restart=30)
+    dH = sp.DeviceHierarchy(amg.hierarchy().levels)
+    dfx = sp.DeviceVector(F.nrow).fill(0.0)
+    it, hist, ok = dH.pgmres(sp.DeviceVector(data=fb), dfx, 1e-8, restart=30)
+    assert ok and abs(it - (len(hp_ref) - 1)) <= 1
+    m = min(len(hist), len(hp_ref))
+    np.testing.assert_allclose(hist[:m], hp_ref[:m], rtol=1e-7, atol=1e-13 * hp_ref[0])
+    assert np.linalg.norm(fb - F.to_scipy() @ dfx.download()) <= 1e-8 * (1 + 1e-6)
+
+
 def test_edge_cases(sp, oracle):
     # 1x1
     A = CSR(1, 1, [0, 1], [0], [2.0])

@@ -179,3 +179,49 @@ def test_sor_vcycle_solver_matches_reference(oracle, fixture_system, golden):
     assert len(hist) - 1 == g["cycles"] == 28
     np.testing.assert_allclose(hist[1:], g["hist"], rtol=1e-10)
     assert np.linalg.norm(b - A.to_scipy() @ x) <= 1e-8
+
+
+def test_gmres_restatement_against_scipy(oracle, fixture_system):
+    """GMRES(m) is not in the reference (F3); the oracle's statement of it is pinned to scipy's on a nonsymmetric
+    matrix (inner-iteration residual estimates), to the minimal-residual property, and to restart behaviour."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+
+    rng = np.random.default_rng(11)
+    n = 300
+    S = sps.diags([-1.3, 2.6, -0.7], [-1, 0, 1], shape=(n, n)) + sps.random(n, n, density=0.01, random_state=3) * 0.2
+    S = S.tocsr()
+    S.sort_indices()
+    A = CSR(n, n, S.indptr, S.indices, S.data)
+    b = rng.standard_normal(n)
+    tol = 1e-9 * np.linalg.norm(b)
+    # full GMRES (restart >= iterations): estimates equal scipy's per-iteration preconditioned-residual norms
+    seen = []
+    xs, info = spla.gmres(S, b, x0=np.zeros(n), rtol=1e-9, atol=0.0, restart=200, maxiter=1,
+                          callback=lambda r: seen.append(r), callback_type="pr_norm")
+    assert info == 0
+    x, hist = oracle.gmres(A, b, np.zeros(n), tol, restart=200, max_iter=200)
+    k = len(hist) - 1
+    assert k == len(seen)
+    np.testing.assert_allclose(hist[1:k] / hist[0], seen[: k - 1], rtol=1e-8)  # scipy reports relative norms
+    assert np.linalg.norm(b - S @ x) <= tol * (1 + 1e-6) and hist[-1] == pytest.approx(np.linalg.norm(b - S @ x), rel=1e-6)
+    # minimal residual over the Krylov space after 7 iterations
+    x7, h7 = oracle.gmres(A, b, np.zeros(n), 0.0, restart=50, max_iter=7)
+    K = np.zeros((n, 7))
+    K[:, 0] = b
+    for j in range(1, 7):
+        K[:, j] = S @ K[:, j - 1]
+    Q, _ = np.linalg.qr(K)
+    c = np.linalg.lstsq(S @ Q, b, rcond=None)[0]
+    assert h7[-1] == pytest.approx(np.linalg.norm(b - S @ (Q @ c)), rel=1e-9)
+    # restarts: still converges, needs at least as many iterations, monotone within a cycle
+    xr, hr = oracle.gmres(A, b, np.zeros(n), tol, restart=10, max_iter=2000)
+    assert len(hr) >= len(hist) and np.linalg.norm(b - S @ xr) <= tol * (1 + 1e-6)
+    assert all(hr[i + 1] <= hr[i] * (1 + 1e-12) for i in range(9))
+    # V-cycle as right preconditioner on the bundled SPD system: far fewer iterations than without
+    F, fb = fixture_system
+    amg = OracleAmg(F)
+    xp, hp = amg.pgmres(fb, np.zeros(F.nrow), 1e-8, restart=30)
+    assert np.linalg.norm(fb - F.to_scipy() @ xp) <= 1e-8 * (1 + 1e-6)
+    _, hpcg = amg.pcg(fb, np.zeros(F.nrow), 1e-8)
+    assert len(hp) - 1 <= len(hpcg) - 1 + 2  # GMRES minimises the residual: no worse than PCG (+restart slack)
