@@ -1,5 +1,6 @@
 #!/bin/bash
-# Developer tool (run under gpurun, one GPU): validate and time the opt-in csr-pattern8 kernel.
+# Developer tool (run under gpurun, one GPU): validate and time the opt-in csr-pattern8 kernel, and give the other
+# not-yet-run additions (smoothed aggregation, GMRES) their first GPU run.
 #   gpurun --timeout 1500 -- 'bash tools/pattern_sweep.sh'
 # 1. opt-in parity tests  2. launch-shape sweep on the 256^3 Jacobi sweep  3. whole-solve bench with the kernel selected
 # 4. one ncu --set full capture of the pattern Jacobi kernel.  Everything lands in gpurun_out/pattern/.
@@ -9,6 +10,11 @@ mkdir -p "$out"
 SPARSH_TEST_PATTERN=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k pattern > "$out/tests.log" 2>&1
 echo "tests exit $?" | tee -a "$out/tests.log"
 grep -q "passed" "$out/tests.log" || { tail -30 "$out/tests.log"; exit 1; }
+# the other two additions that have not had a GPU run yet: smoothed-aggregation hierarchies and GMRES(m)
+SPARSH_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "smoothed_aggregation or gmres" \
+  > "$out/tests_experimental.log" 2>&1
+echo "experimental tests exit $?" | tee -a "$out/tests_experimental.log"
+tail -5 "$out/tests_experimental.log"
 for rpt in 2 4 8; do
   for jb in 2 4; do
     [ "$rpt" = 8 ] && [ "$jb" = 4 ] && continue
