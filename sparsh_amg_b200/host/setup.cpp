@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <numeric>
 #include <vector>
 
@@ -421,59 +422,112 @@ void SA_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int level) {
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
+// intermediate CSR whose index/value arrays are allocated WITHOUT being zero-filled: the threads that compute the
+// entries are the first to touch the pages (a std::vector would fault in and clear gigabytes on one thread first)
 struct Csr {
     int nrow = 0, ncol = 0;
-    std::vector<int> rp, ci;
-    std::vector<double> v;
+    std::vector<int> rp;
+    std::unique_ptr<int[]> ci;
+    std::unique_ptr<double[]> v;
+    void alloc(size_t nnz) {
+        ci.reset(new int[std::max<size_t>(nnz, 1)]);
+        v.reset(new double[std::max<size_t>(nnz, 1)]);
+    }
 };
 
-// row-wise (Gustavson) C = A * B with a dense position table per thread; the entries of a C row appear in first-touch
-// order and each is accumulated in traversal order, which fixes the rounding independently of the thread count
+// row-wise (Gustavson) C = A * B.  The entries of a C row appear in first-touch order and each is accumulated in
+// traversal order, which fixes the rounding independently of the thread count.  Rows of the Galerkin products are
+// short (tens of entries), so the accumulator of a row is a small list searched linearly — it stays in L1, where a
+// dense position table of B's width per thread (tens of MB at 256^3) misses on every touch; rows that outgrow the
+// list fall back to such a table, allocated by the thread on first need.  Same order either way.
 void spgemm(int arow, const int *arp, const int *aci, const double *av, int bcol, const int *brp, const int *bci,
             const double *bv, Csr &C) {
+    constexpr int SMALL = 96;
     C.nrow = arow;
     C.ncol = bcol;
     C.rp.assign((size_t)arow + 1, 0);
     const int nt = options().threads;
 #pragma omp parallel num_threads(nt)
     {
-        std::vector<int> mark((size_t)std::max(bcol, 1), -1);
+        std::vector<int> mark;  // dense fallback
+        int list[SMALL];
 #pragma omp for schedule(dynamic, 4096)
         for (int i = 0; i < arow; i++) {
             int cnt = 0;
-            for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+            bool dense = false;
+            for (int ja = arp[i]; ja < arp[i + 1] && !dense; ja++) {
                 const int k = aci[ja];
-                for (int jb = brp[k]; jb < brp[k + 1]; jb++)
-                    if (mark[bci[jb]] != i) {
-                        mark[bci[jb]] = i;
-                        cnt++;
+                for (int jb = brp[k]; jb < brp[k + 1]; jb++) {
+                    const int c = bci[jb];
+                    int t = 0;
+                    while (t < cnt && list[t] != c) t++;
+                    if (t == cnt) {
+                        if (cnt == SMALL) {
+                            dense = true;
+                            break;
+                        }
+                        list[cnt++] = c;
                     }
+                }
+            }
+            if (dense) {
+                if (mark.empty()) mark.assign((size_t)std::max(bcol, 1), -1);
+                cnt = 0;
+                for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+                    const int k = aci[ja];
+                    for (int jb = brp[k]; jb < brp[k + 1]; jb++)
+                        if (mark[bci[jb]] != i) {
+                            mark[bci[jb]] = i;
+                            cnt++;
+                        }
+                }
             }
             C.rp[i + 1] = cnt;
         }
     }
     for (int i = 0; i < arow; i++) C.rp[i + 1] += C.rp[i];
-    C.ci.resize((size_t)std::max(C.rp[arow], 1));
-    C.v.resize((size_t)std::max(C.rp[arow], 1));
+    C.alloc((size_t)C.rp[arow]);
 #pragma omp parallel num_threads(nt)
     {
-        std::vector<int> pos((size_t)std::max(bcol, 1), -1);
+        std::vector<int> pos;  // dense fallback: position of a column inside the current row, valid when >= base
 #pragma omp for schedule(dynamic, 4096)
         for (int i = 0; i < arow; i++) {
-            const int base = C.rp[i];
-            int o = base;
-            for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
-                const int k = aci[ja];
-                const double a = av[ja];
-                for (int jb = brp[k]; jb < brp[k + 1]; jb++) {
-                    const int c = bci[jb];
-                    if (pos[c] < base) {
-                        pos[c] = o;
-                        C.ci[o] = c;
-                        C.v[o] = a * bv[jb];
-                        o++;
-                    } else {
-                        C.v[pos[c]] += a * bv[jb];
+            const int base = C.rp[i], len = C.rp[i + 1] - base;
+            int *cc = C.ci.get() + base;
+            double *cv = C.v.get() + base;
+            int o = 0;
+            if (len <= SMALL) {
+                for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+                    const int k = aci[ja];
+                    const double a = av[ja];
+                    for (int jb = brp[k]; jb < brp[k + 1]; jb++) {
+                        const int c = bci[jb];
+                        int t = 0;
+                        while (t < o && cc[t] != c) t++;
+                        if (t == o) {
+                            cc[o] = c;
+                            cv[o] = a * bv[jb];
+                            o++;
+                        } else {
+                            cv[t] += a * bv[jb];
+                        }
+                    }
+                }
+            } else {
+                if (pos.empty()) pos.assign((size_t)std::max(bcol, 1), -1);
+                for (int ja = arp[i]; ja < arp[i + 1]; ja++) {
+                    const int k = aci[ja];
+                    const double a = av[ja];
+                    for (int jb = brp[k]; jb < brp[k + 1]; jb++) {
+                        const int c = bci[jb];
+                        if (pos[c] < base) {
+                            pos[c] = base + o;
+                            cc[o] = c;
+                            cv[o] = a * bv[jb];
+                            o++;
+                        } else {
+                            cv[pos[c] - base] += a * bv[jb];
+                        }
                     }
                 }
             }
@@ -481,22 +535,33 @@ void spgemm(int arow, const int *arp, const int *aci, const double *av, int bcol
     }
 }
 
+// T = M^T, stable: row c of T lists the rows of M in ascending order.  Every thread owns a contiguous range of T's rows
+// and scans all entries of M in order, keeping those that fall into its range — nt reads of the (small) index array
+// instead of one sequential counting sort.
 void transpose(int nrow, int ncol, const int *rp, const int *ci, const double *v, Csr &T) {
     const int nnz = rp[nrow];
     T.nrow = ncol;
     T.ncol = nrow;
     T.rp.assign((size_t)ncol + 1, 0);
-    T.ci.resize((size_t)std::max(nnz, 1));
-    T.v.resize((size_t)std::max(nnz, 1));
+    T.alloc((size_t)nnz);
     for (int j = 0; j < nnz; j++) T.rp[ci[j] + 1]++;
     for (int c = 0; c < ncol; c++) T.rp[c + 1] += T.rp[c];
-    std::vector<int> cur(T.rp.begin(), T.rp.end() - 1);
-    for (int i = 0; i < nrow; i++)
-        for (int j = rp[i]; j < rp[i + 1]; j++) {
-            const int d = cur[ci[j]]++;
-            T.ci[d] = i;
-            T.v[d] = v[j];
-        }
+    const int nt = std::max(1, options().threads);
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num(), n_t = omp_get_num_threads();
+        const int c0 = (int)((long long)ncol * t / n_t), c1 = (int)((long long)ncol * (t + 1) / n_t);
+        std::vector<int> cur(T.rp.begin() + c0, T.rp.begin() + c1);
+        for (int i = 0; i < nrow; i++)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                const int c = ci[j];
+                if (c >= c0 && c < c1) {
+                    const int d = cur[c - c0]++;
+                    T.ci[d] = i;
+                    T.v[d] = v[j];
+                }
+            }
+    }
 }
 
 }  // namespace
@@ -506,16 +571,30 @@ namespace parallel {
 // Ac = P^T (A P), columns sorted, diagonal extracted
 void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
     Csr AP, R, C;
+    const bool tm = getenv("SPARSH_SETUP_TIMING") != nullptr;
+    double t0 = omp_get_wtime();
     spgemm(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, AP);
+    double t1 = omp_get_wtime();
     transpose(P1.nrow, P1.ncol, P1.rowptr, P1.colindex, P1.val, R);
-    spgemm(R.nrow, R.rp.data(), R.ci.data(), R.v.data(), P1.ncol, AP.rp.data(), AP.ci.data(), AP.v.data(), C);
+    double t2 = omp_get_wtime();
+    spgemm(R.nrow, R.rp.data(), R.ci.get(), R.v.get(), P1.ncol, AP.rp.data(), AP.ci.get(), AP.v.get(), C);
+    double t3 = omp_get_wtime();
     const int nc = P1.ncol, cnnz = C.rp[nc];
-    Ac = new sp_matrix_mg(nc, nc, cnnz);
+    Ac = new sp_matrix_mg();  // adopts the product's arrays (both sides use new[] / delete[])
+    Ac->nrow = nc;
+    Ac->ncol = nc;
+    Ac->nnz = cnnz;
+    Ac->rowptr = new int[(size_t)nc + 1];
     std::copy(C.rp.begin(), C.rp.end(), Ac->rowptr);
-    std::copy(C.ci.begin(), C.ci.begin() + cnnz, Ac->colindex);
-    std::copy(C.v.begin(), C.v.begin() + cnnz, Ac->val);
+    Ac->colindex = C.ci.release();
+    Ac->val = C.v.release();
+    double t4 = omp_get_wtime();
     Ac->sp_matrix_fill();
+    double t5 = omp_get_wtime();
     Ac->sp_matrix_fill_diagonal();
+    if (tm)
+        std::cout << "  RAP: A*P " << t1 - t0 << " transpose " << t2 - t1 << " R*(AP) " << t3 - t2 << " alloc+copy " << t4 - t3
+                  << " sort " << t5 - t4 << " diag " << omp_get_wtime() - t5 << std::endl;
 }
 
 // reference src/AMG_cycle_utilities.cpp:149-188: the columns of P follow the coarse matrix' colour permutation,
