@@ -210,7 +210,13 @@ static sp_matrix_mg *gen_7pt(int nx, int ny, int nz, double diag) {
         rp[i + 1] = 1 + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
     }
     for (long i = 0; i < n; i++) rp[i + 1] += rp[i];
-    sp_matrix_mg *A = new sp_matrix_mg((int)n, (int)n, rp[n]);
+    // arrays allocated without the constructor's zero fill: the generating threads are the first to touch the pages
+    sp_matrix_mg *A = new sp_matrix_mg();
+    A->nrow = A->ncol = (int)n;
+    A->nnz = rp[n];
+    A->rowptr = new int[(size_t)n + 1];
+    A->colindex = new int[(size_t)std::max(rp[n], 1)];
+    A->val = new double[(size_t)std::max(rp[n], 1)];
     std::copy(rp.begin(), rp.end(), A->rowptr);
     const long plane = (long)nx * ny;
 #pragma omp parallel for num_threads(options().threads) schedule(static)
