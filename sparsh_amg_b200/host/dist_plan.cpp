@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <vector>
 
@@ -185,21 +187,31 @@ void build_op(int nrow_g, const int *rp, const int *ci, const double *v, const d
     op.ie = best_e;
 }
 
+// stable transpose (row c lists the source rows ascending); every thread owns a contiguous range of output rows and
+// scans the entries in order; output arrays are not zero-filled first (see host/setup.cpp: transpose)
 void transpose_csr(int nrow, int ncol, const int *rp, const int *ci, const double *v, std::vector<int> &trp,
-                   std::vector<int> &tci, std::vector<double> &tv) {
+                   std::unique_ptr<int[]> &tci, std::unique_ptr<double[]> &tv) {
     const int nnz = rp[nrow];
     trp.assign((size_t)ncol + 1, 0);
-    tci.resize((size_t)std::max(nnz, 1));
-    tv.resize((size_t)std::max(nnz, 1));
+    tci.reset(new int[(size_t)std::max(nnz, 1)]);
+    tv.reset(new double[(size_t)std::max(nnz, 1)]);
     for (int j = 0; j < nnz; j++) trp[ci[j] + 1]++;
     for (int c = 0; c < ncol; c++) trp[c + 1] += trp[c];
-    std::vector<int> cur(trp.begin(), trp.end() - 1);
-    for (int i = 0; i < nrow; i++)
-        for (int j = rp[i]; j < rp[i + 1]; j++) {
-            const int d = cur[ci[j]]++;
-            tci[d] = i;
-            tv[d] = v[j];
-        }
+#pragma omp parallel num_threads(std::max(1, options().threads))
+    {
+        const int t = omp_get_thread_num(), n_t = omp_get_num_threads();
+        const int c0 = (int)((long long)ncol * t / n_t), c1 = (int)((long long)ncol * (t + 1) / n_t);
+        std::vector<int> cur(trp.begin() + c0, trp.begin() + c1);
+        for (int i = 0; i < nrow; i++)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                const int c = ci[j];
+                if (c >= c0 && c < c1) {
+                    const int d = cur[c - c0]++;
+                    tci[d] = i;
+                    tv[d] = v[j];
+                }
+            }
+    }
 }
 
 }  // namespace
@@ -210,6 +222,7 @@ extern "C" {
 // is always distributed)
 void *sparsh_host_dist_plan(void *Sv, int nranks, int rank, int tail_threshold) {
     AMG_solver *S = (AMG_solver *)Sv;
+    const double t_begin = omp_get_wtime();
     DistPlan *pl = new DistPlan();
     pl->nranks = nranks;
     pl->rank = rank;
@@ -244,18 +257,29 @@ void *sparsh_host_dist_plan(void *Sv, int nranks, int rank, int tail_threshold) 
             if (o < 0) o = 0;  // a coarse row nobody interpolates from (cannot happen with HEM/Beck)
         finish_space(sp[l + 1], nranks);
     }
+    const bool tm = getenv("SPARSH_SETUP_TIMING") != nullptr;
+    const double ts = omp_get_wtime();
+    if (tm) std::printf("  plan: index spaces %.3f s\n", ts - t_begin);
     pl->lev.resize(nd);
     for (int l = 0; l < nd; l++) {
         const sp_matrix_mg *A = S->Av[l], *P = S->Pv[l];
         LevelLocal &L = pl->lev[l];
+        const double t0 = omp_get_wtime();
         for (int g = 0; g < A->nrow; g++)
             if (sp[l].owner[g] == rank) L.rows.push_back(g);
         build_op(A->nrow, A->rowptr, A->colindex, A->val, A->diagonal, sp[l], sp[l], nranks, rank, L.A);
+        const double t1 = omp_get_wtime();
         build_op(P->nrow, P->rowptr, P->colindex, P->val, nullptr, sp[l], sp[l + 1], nranks, rank, L.P);
-        std::vector<int> trp, tci;
-        std::vector<double> tv;
+        const double t2 = omp_get_wtime();
+        std::vector<int> trp;
+        std::unique_ptr<int[]> tci;
+        std::unique_ptr<double[]> tv;
         transpose_csr(P->nrow, P->ncol, P->rowptr, P->colindex, P->val, trp, tci, tv);
-        build_op(P->ncol, trp.data(), tci.data(), tv.data(), nullptr, sp[l + 1], sp[l], nranks, rank, L.R);
+        const double t3 = omp_get_wtime();
+        build_op(P->ncol, trp.data(), tci.get(), tv.get(), nullptr, sp[l + 1], sp[l], nranks, rank, L.R);
+        if (tm)
+            std::printf("  plan: level %d A %.3f P %.3f transpose %.3f R %.3f s\n", l, t1 - t0, t2 - t1, t3 - t2,
+                        omp_get_wtime() - t3);
     }
     pl->tail_counts = sp[nd].count;
     pl->tail_rows.clear();
