@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -80,35 +81,91 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
 }
 
 // csr-dict16 twin: dictionaries of the distinct values and of the distinct (col - row) offsets, one 16-bit code per
-// entry.  The encoder is host-only; false when either dictionary would need more than 256 entries.
+// entry.  The encoder is host-only; false when either dictionary would need more than 256 entries.  Row chunks are
+// scanned by a few threads: local dictionaries in order of first appearance, merged in chunk order (so the result is
+// the one a sequential scan produces), then the codes are written in parallel.
+struct LocalDict {
+    std::vector<double> val;
+    std::vector<int> off;
+    bool overflow = false;
+};
+inline int find_bits(const std::vector<double> &d, double x, int hint) {
+    if (hint < (int)d.size() && std::memcmp(&d[hint], &x, sizeof x) == 0) return hint;
+    for (int k = 0; k < (int)d.size(); k++)
+        if (std::memcmp(&d[k], &x, sizeof x) == 0) return k;  // bit pattern: -0.0 and NaNs stay themselves
+    return -1;
+}
+inline int find_int(const std::vector<int> &d, int x, int hint) {
+    if (hint < (int)d.size() && d[hint] == x) return hint;
+    for (int k = 0; k < (int)d.size(); k++)
+        if (d[k] == x) return k;
+    return -1;
+}
 bool dict_encode(int n, const int *rp, const int *ci, const double *v, unsigned short *code, std::vector<double> &dv,
                  std::vector<int> &dof) {
-    int last_v = 0, last_o = 0;
-    for (int i = 0; i < n; i++)
-        for (int j = rp[i]; j < rp[i + 1]; j++) {
-            const double val = v[j];
-            const int off = ci[j] - i;
-            int vi = -1, oi = -1;
-            if (!dv.empty() && std::memcmp(&dv[last_v], &val, sizeof val) == 0) vi = last_v;
-            for (int k = 0; vi < 0 && k < (int)dv.size(); k++)
-                if (std::memcmp(&dv[k], &val, sizeof val) == 0) vi = k;  // bit pattern: -0.0 and NaNs stay themselves
-            if (vi < 0) {
+    const size_t nnz = (size_t)rp[n];
+    int nt = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (nnz < (size_t)1 << 20) nt = 1;
+    auto row_begin = [&](int t) { return (int)((long long)n * t / nt); };
+    std::vector<LocalDict> loc((size_t)nt);
+    auto scan = [&](int t) {
+        LocalDict &L = loc[t];
+        int hv = 0, ho = 0;
+        for (int i = row_begin(t); i < row_begin(t + 1) && !L.overflow; i++)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                int vi = find_bits(L.val, v[j], hv), oi = find_int(L.off, ci[j] - i, ho);
+                if (vi < 0) {
+                    if (L.val.size() == 256) {
+                        L.overflow = true;
+                        break;
+                    }
+                    L.val.push_back(v[j]);
+                    vi = (int)L.val.size() - 1;
+                }
+                if (oi < 0) {
+                    if (L.off.size() == 256) {
+                        L.overflow = true;
+                        break;
+                    }
+                    L.off.push_back(ci[j] - i);
+                    oi = (int)L.off.size() - 1;
+                }
+                hv = vi;
+                ho = oi;
+            }
+    };
+    auto run = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    run(scan);
+    dv.clear();
+    dof.clear();
+    for (const LocalDict &L : loc) {
+        if (L.overflow) return false;
+        for (double x : L.val)
+            if (find_bits(dv, x, 0) < 0) {
                 if (dv.size() == 256) return false;
-                dv.push_back(val);
-                vi = (int)dv.size() - 1;
+                dv.push_back(x);
             }
-            if (!dof.empty() && dof[last_o] == off) oi = last_o;
-            for (int k = 0; oi < 0 && k < (int)dof.size(); k++)
-                if (dof[k] == off) oi = k;
-            if (oi < 0) {
+        for (int x : L.off)
+            if (find_int(dof, x, 0) < 0) {
                 if (dof.size() == 256) return false;
-                dof.push_back(off);
-                oi = (int)dof.size() - 1;
+                dof.push_back(x);
             }
-            last_v = vi;
-            last_o = oi;
-            code[j] = (unsigned short)((vi << 8) | oi);
-        }
+    }
+    auto write = [&](int t) {
+        int hv = 0, ho = 0;
+        for (int i = row_begin(t); i < row_begin(t + 1); i++)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                hv = find_bits(dv, v[j], hv);
+                ho = find_int(dof, ci[j] - i, ho);
+                code[j] = (unsigned short)((hv << 8) | ho);
+            }
+    };
+    run(write);
     return true;
 }
 
