@@ -255,6 +255,14 @@ def test_csr_dict16_encoding_is_lossless(host, fixture_system):
         assert np.array_equal(dval[code >> 8].view(np.uint64), np.ascontiguousarray(M.val).view(np.uint64))
         assert np.array_equal(rows + doff[code & 255], M.colindex)
     assert representable >= 2
+    # large enough for the multi-threaded scan: dictionaries still come out in order of first appearance
+    B = poisson_7pt(70, 64, 60)
+    code, dval, doff = _dict_encode(B)
+    rows = np.repeat(np.arange(B.nrow, dtype=np.int64), np.diff(B.rowptr))
+    for got, seq in ((dval, B.val), (doff, B.colindex - rows)):
+        _, first = np.unique(seq, return_index=True)
+        np.testing.assert_array_equal(got, seq[np.sort(first)])
+    assert np.array_equal(dval[code >> 8], B.val) and np.array_equal(rows + doff[code & 255], B.colindex)
     # -0.0 and 0.0 are different dictionary entries (bit pattern, not ==)
     Z = HostCSR(2, 2, [0, 1, 2], [0, 1], [0.0, -0.0])
     code, dval, _ = _dict_encode(Z)
