@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -95,23 +96,34 @@ int sparsh_host_amg_save(void *Sv, const char *dir_c) {
     std::ofstream meta(dir + "/meta.txt");
     if (!meta) return -1;
     meta << (S->l + 1) << "\n";
+    struct Job {
+        std::string path;
+        const void *ptr;
+        size_t bytes;
+    };
+    std::vector<Job> jobs;
     for (int k = 0; k <= S->l; k++) {
         const sp_matrix_mg *A = S->Av[k];
         const int nnz = A->rowptr[A->nrow];
         const int pncol = k < S->l ? S->Pv[k]->ncol : 0, pnnz = k < S->l ? S->Pv[k]->rowptr[S->Pv[k]->nrow] : 0;
         meta << A->nrow << " " << nnz << " " << pncol << " " << pnnz << "\n";
-        bool ok = write_file(name(dir, "A", k, "rp"), A->rowptr, sizeof(int) * ((size_t)A->nrow + 1)) &&
-                  write_file(name(dir, "A", k, "ci"), A->colindex, sizeof(int) * (size_t)nnz) &&
-                  write_file(name(dir, "A", k, "v"), A->val, sizeof(double) * (size_t)nnz) &&
-                  write_file(name(dir, "A", k, "d"), A->diagonal, sizeof(double) * (size_t)A->nrow);
-        if (ok && k < S->l) {
+        jobs.push_back({name(dir, "A", k, "rp"), A->rowptr, sizeof(int) * ((size_t)A->nrow + 1)});
+        jobs.push_back({name(dir, "A", k, "ci"), A->colindex, sizeof(int) * (size_t)nnz});
+        jobs.push_back({name(dir, "A", k, "v"), A->val, sizeof(double) * (size_t)nnz});
+        jobs.push_back({name(dir, "A", k, "d"), A->diagonal, sizeof(double) * (size_t)A->nrow});
+        if (k < S->l) {
             const sp_matrix_mg *P = S->Pv[k];
-            ok = write_file(name(dir, "P", k, "rp"), P->rowptr, sizeof(int) * ((size_t)P->nrow + 1)) &&
-                 write_file(name(dir, "P", k, "ci"), P->colindex, sizeof(int) * (size_t)pnnz) &&
-                 write_file(name(dir, "P", k, "v"), P->val, sizeof(double) * (size_t)pnnz);
+            jobs.push_back({name(dir, "P", k, "rp"), P->rowptr, sizeof(int) * ((size_t)P->nrow + 1)});
+            jobs.push_back({name(dir, "P", k, "ci"), P->colindex, sizeof(int) * (size_t)pnnz});
+            jobs.push_back({name(dir, "P", k, "v"), P->val, sizeof(double) * (size_t)pnnz});
         }
-        if (!ok) return -2;
     }
+    // the files are independent: several writers (the biggest arrays are listed first, dynamic schedule)
+    int failed = 0;
+#pragma omp parallel for num_threads(std::max(1, sparsh::options().threads)) schedule(dynamic, 1) reduction(+ : failed)
+    for (int j = 0; j < (int)jobs.size(); j++)
+        if (!write_file(jobs[j].path, jobs[j].ptr, jobs[j].bytes)) failed++;
+    if (failed) return -2;
     meta.close();
     return meta ? 0 : -3;
 }
