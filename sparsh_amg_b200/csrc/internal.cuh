@@ -91,6 +91,8 @@ struct PatView {
     const double *__restrict__ pdiag;       // n_pat: the row's diagonal as sp_matrix_fill_diagonal extracts it
     int n_pat, n_ent;
     int use_pdiag;  // the epilogue's d[] is this matrix' own diagonal: take it from the table
+    int far_off;    // largest positive offset of the table (0: none): the only x line of a row that rows swept earlier
+                    // have not pulled into L2 yet — prefetched while the pattern byte is still on its way
 };
 constexpr int PAT_ESCAPE = 255;    // pattern id of an escape row
 constexpr int PAT_MAX_ENT = 2048;  // table entries over all patterns (32 KB)
@@ -130,10 +132,10 @@ struct sparsh_matrix_s {
     sparsh::PatEntry *pat_ent = nullptr;
     int *pat_start = nullptr;
     double *pat_diag = nullptr;
-    int n_pat = 0, n_pent = 0, n_escape = 0;
+    int n_pat = 0, n_pent = 0, n_escape = 0, pat_far = 0;
     bool has_pat = false;
     sparsh::PatView pattern(bool use_pdiag) const {
-        return sparsh::PatView{pat, pat_ent, pat_start, pat_diag, n_pat, n_pent, use_pdiag ? 1 : 0};
+        return sparsh::PatView{pat, pat_ent, pat_start, pat_diag, n_pat, n_pent, use_pdiag ? 1 : 0, pat_far};
     }
     sparsh::CsrView view() const { return sparsh::CsrView{nrow, ncol, nnz, rowptr, col, val}; }
     sparsh::DictView dict() const { return sparsh::DictView{code, dict_val, dict_off, n_dval, n_doff}; }

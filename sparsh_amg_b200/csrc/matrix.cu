@@ -348,6 +348,8 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     A->n_pat = n_pat;
     A->n_pent = n_ent;
     A->n_escape = T.n_escape;
+    A->pat_far = 0;
+    for (int k = 0; k < n_ent; k++) A->pat_far = std::max(A->pat_far, T.off[k]);
     A->has_pat = true;
     return true;
 }

@@ -409,8 +409,12 @@ __global__ void __launch_bounds__(THREADS)
 // pattern — the common case — reads each entry as one broadcast).  No matrix stream is left to stage: per
 // row the kernel moves the pattern byte, the vector operands and the result, which is what bounds it.  Thread t owns
 // rows r0 + s*THREADS + t (s < RPT); all their pattern bytes and per-row operands are requested before the table copy
-// is waited for.  Escape rows (id 255) are walked from the resident CSR arrays.
+// is waited for, together with an L2 prefetch of the one x line per row that no earlier row has touched (offset
+// far_off: the next grid plane), so that the gathers that follow the table look-up find everything in L1/L2.
+// Escape rows (id 255) are walked from the resident CSR arrays.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int THREADS, int RPT, int JB, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_pattern_kernel(CsrView A, PatView P, const double *x, double *y, EpiArgs args, RowRange rr, double *partials,
@@ -436,6 +440,8 @@ __global__ void __launch_bounds__(THREADS)
             const int row = r0 + s * THREADS + tid;
             pid[s] = P.pat[row];
             e[s] = epi_load<EPI, false>(args, y, row);
+            // one lane in 16 (= one per 128-byte line) asks L2 for the far line its rows will gather from
+            if (P.far_off > 0 && (row & 15) == 0 && row + P.far_off < A.ncol) prefetch_l2(x + row + P.far_off);
         }
     }
     for (int i = tid; i < P.n_ent; i += THREADS) {
