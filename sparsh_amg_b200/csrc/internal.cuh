@@ -94,6 +94,19 @@ struct PatView {
     int far_off;    // largest positive offset of the table (0: none): the only x line of a row that rows swept earlier
                     // have not pulled into L2 yet — prefetched while the pattern byte is still on its way
 };
+// x windows of the TMA-staged pattern kernel: a tile of PAT_TILE consecutive rows gathers x only from a few contiguous
+// index ranges [r0 + lo_w, r0 + lo_w + len_w) — one per group of table offsets that lie within a tile length of each
+// other — which one thread fetches with bulk copies.  win[k] tells which window serves table entry k.
+constexpr int PAT_TILE = 512;
+constexpr int PAT_MAX_WIN = 8;
+constexpr int PAT_WIN_DOUBLES = 3072;  // sum of the window lengths that still leaves >= 6 tiles resident per SM
+struct PatWindows {
+    int nwin;
+    int lo[PAT_MAX_WIN], len[PAT_MAX_WIN];  // len is even
+    int total;                              // sum of (len + 2): doubles of shared memory
+    int w0;                                 // window that contains offset 0 (-1: none)
+    const unsigned char *__restrict__ win;  // n_ent
+};
 constexpr int PAT_ESCAPE = 255;    // pattern id of an escape row
 constexpr int PAT_MAX_ENT = 2048;  // table entries over all patterns (32 KB)
 constexpr int PAT_MAX_ROW = 64;    // longer rows are never tabulated
@@ -134,6 +147,8 @@ struct sparsh_matrix_s {
     double *pat_diag = nullptr;
     int n_pat = 0, n_pent = 0, n_escape = 0, pat_far = 0;
     bool has_pat = false;
+    sparsh::PatWindows pat_windows = {};  // nwin == 0: the TMA-staged variant does not apply
+    unsigned char *pat_win = nullptr;
     sparsh::PatView pattern(bool use_pdiag) const {
         return sparsh::PatView{pat, pat_ent, pat_start, pat_diag, n_pat, n_pent, use_pdiag ? 1 : 0, pat_far};
     }

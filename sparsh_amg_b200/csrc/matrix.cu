@@ -350,6 +350,46 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     A->n_escape = T.n_escape;
     A->pat_far = 0;
     for (int k = 0; k < n_ent; k++) A->pat_far = std::max(A->pat_far, T.off[k]);
+    // x windows for the TMA-staged variant: distinct offsets, ascending, merged while the gap is at most a tile
+    {
+        std::vector<int> offs(T.off.begin(), T.off.end());
+        std::sort(offs.begin(), offs.end());
+        offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+        PatWindows W = {};
+        W.w0 = -1;
+        std::vector<int> hi;  // largest offset of each window
+        bool fits = !offs.empty();
+        for (size_t q = 0; q < offs.size() && fits; q++) {
+            if (W.nwin > 0 && (long long)offs[q] - hi.back() <= PAT_TILE) {
+                hi.back() = offs[q];
+            } else if (W.nwin == PAT_MAX_WIN) {
+                fits = false;
+            } else {
+                W.lo[W.nwin++] = offs[q];
+                hi.push_back(offs[q]);
+            }
+        }
+        for (int w = 0; w < W.nwin && fits; w++) {
+            const long long len = (long long)hi[w] - W.lo[w] + PAT_TILE;
+            W.len[w] = (int)((len + 1) & ~1LL);
+            W.total += W.len[w] + 2;
+            if (W.lo[w] <= 0 && hi[w] >= 0) W.w0 = w;
+        }
+        fits = fits && W.total <= PAT_WIN_DOUBLES;
+        if (fits) {
+            std::vector<unsigned char> win((size_t)n_ent + 1, 0);
+            for (int k = 0; k < n_ent; k++)
+                for (int w = 0; w < W.nwin; w++)
+                    if (T.off[k] >= W.lo[w] && T.off[k] <= hi[w]) win[k] = (unsigned char)w;
+            if (cudaMalloc(&A->pat_win, win.size()) == cudaSuccess &&
+                cudaMemcpy(A->pat_win, win.data(), win.size(), cudaMemcpyHostToDevice) == cudaSuccess) {
+                W.win = A->pat_win;
+                A->pat_windows = W;
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     A->has_pat = true;
     return true;
 }
@@ -464,6 +504,7 @@ int sparsh_matrix_destroy(sparsh_matrix_t A) {
     cudaFree(A->pat_ent);
     cudaFree(A->pat_start);
     cudaFree(A->pat_diag);
+    cudaFree(A->pat_win);
     delete A;
     return SPARSH_OK;
 }
