@@ -99,6 +99,13 @@ int sparsh_pattern_encode(int nrow, int ncol, int nnz, const int *h_rowptr, cons
                           const double *h_val, const double *h_diag, unsigned char *pat, double *ent_val,
                           int *ent_off, int *start, int *n_pat, int *n_escape);
 
+/* x windows of the TMA-staged csr-pattern8 kernel (host-only helper, so the tiling arithmetic can be checked without a
+ * GPU): a tile of *tile consecutive rows gathers x only from *nwin contiguous ranges [r0 + lo[w], r0 + lo[w] + len[w]),
+ * one per group of table offsets that lie within a tile length of each other; win[k] names the window of table entry k,
+ * *w0 the window that holds offset 0 (-1: none).  lo/len need 8 slots.  *nwin == 0: the variant does not apply. */
+int sparsh_pattern_windows(int n_ent, const int *ent_off, int *tile, int *nwin, int *lo, int *len, int *w0,
+                           unsigned char *win);
+
 /* ------------------------------------------------------------------ per-op ----- */
 /* K9  y = A x                              cusparseDcsrmv, e.g. src/AMG_main_solvers.cu:100,221,354 */
 int sparsh_spmv(sparsh_matrix_t A, const double *d_x, double *d_y);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "sparsh_matrix_force_kernel": (_i, [_vp, _i, _i]),
     "sparsh_pattern_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p,
                                    c_int_p]),
+    "sparsh_pattern_windows": (_i, [_i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, _vp]),
     "sparsh_dict_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p]),
     "sparsh_spmv": (_i, [_vp, _vp, _vp]),
     "sparsh_spmv_dot": (_i, [_vp, _vp, _vp, _vp]),
