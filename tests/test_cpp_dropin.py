@@ -26,6 +26,18 @@ def test_reference_style_caller_compiles_and_links():
     assert os.path.exists(EXE)
 
 
+def test_additions_example_compiles_and_links(tmp_path):
+    """smoothed aggregation, GMRES and the extra readers are reachable from the same header"""
+    lib = os.path.join(ROOT, "sparsh_amg_b200", "lib")
+    exe = str(tmp_path / "additions_main")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "sparsh_amg_b200", "host"),
+           os.path.join(ROOT, "examples", "additions_main.cpp"), "-o", exe, "-L", lib, "-lsparsh_amg", "-lsparsh_b200",
+           f"-Wl,-rpath,{lib}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert subprocess.run([exe], capture_output=True).returncode == 2  # usage message without a GPU or arguments
+
+
 @pytest.mark.gpu
 def test_reference_style_caller_runs(tmp_path, fixture_system, golden):
     build()
