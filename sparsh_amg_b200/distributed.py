@@ -279,7 +279,14 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
             rr = rr.cpu().numpy()
             m = rr >= 0
             x_full[rr[m]] = xr.cpu().numpy()[m]
-        r_true = float(np.linalg.norm(np.ones(n) - A.times(x_full)))
+        if A is not None:
+            Ax = A.times(x_full)
+        else:  # shared hierarchy: level 0 lives in the mapped files
+            import scipy.sparse as sps
+
+            L0 = amg.levels()[0]["A"]
+            Ax = sps.csr_matrix((L0.val, L0.colindex, L0.rowptr), shape=(n, n)) @ x_full
+        r_true = float(np.linalg.norm(np.ones(n) - Ax))
         # roofline of the dominant kernel on this rank's block of the finest level (interior rows of a Jacobi sweep)
         peak, peak_kind = measured_peak()
         line = {"metric": METRIC, "value": solve_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
