@@ -162,9 +162,11 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
         shm = os.path.join(base, f"sparsh_hier_{os.environ.get('MASTER_PORT', '0')}_{grid}")
         A = amg = None
         if rank == 0:
+            host.set_options(threads=os.cpu_count() or 1)  # the other ranks are waiting: all cores to the one setup
             A = host.HostMatrix.poisson3d(grid, grid, grid)
             amg = host.HostAmg(A)
             amg.save(shm)
+            host.set_options(threads=threads)
             amg.free()  # rank 0 drops its private copy too: one copy of the hierarchy per node, in the page cache
             A.free()
             A = None
