@@ -131,6 +131,38 @@ def init_comm(torch_dist, rank, world, device):
     check(lib.sparsh_dist_init(raw, world, rank))
 
 
+def host_hierarchy(grid, rank, threads, share, barrier):
+    """(A, amg, shm_dir) for bench_main.  share=False: every rank builds its own copy (A is the level-0 matrix).
+    share=True: rank 0 builds the hierarchy once with all cores, publishes it as files and drops its private copy; every
+    rank (0 included) maps the files read-only (host/share.cpp) — one copy per node in the page cache; A is None.
+    Needed beyond 256^3: at 512^3 eight private copies (8 x 28 GB) do not fit in a box's RAM."""
+    if not share:
+        A = host.HostMatrix.poisson3d(grid, grid, grid)
+        return A, host.HostAmg(A), None  # (sequential) host hierarchy on every rank; only its part goes to the GPU
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    shm = os.path.join(base, f"sparsh_hier_{os.environ.get('MASTER_PORT', '0')}_{grid}")
+    if rank == 0:
+        host.set_options(threads=os.cpu_count() or 1)  # the other ranks are waiting: all cores to the one setup
+        A = host.HostMatrix.poisson3d(grid, grid, grid)
+        amg = host.HostAmg(A)
+        amg.save(shm)
+        amg.free()
+        A.free()
+        host.set_options(threads=threads)
+    barrier()
+    return None, host.HostAmg.load(shm), shm
+
+
+def level0_times(A, amg, x):
+    """A_0 x on the host (true-residual check outside the timed region); A is None with a shared hierarchy"""
+    if A is not None:
+        return A.times(x)
+    import scipy.sparse as sps
+
+    L0 = amg.levels()[0]["A"]
+    return sps.csr_matrix((L0.val, L0.colindex, L0.rowptr), shape=(L0.nrow, L0.nrow)) @ x
+
+
 def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
     """bench.py --gpus N (N > 1), launched by torchrun: strong scaling of the same solve, rows split across ranks"""
     import torch
@@ -154,27 +186,7 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
     host.set_options(threads=threads, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7, use_graph=1,
                      halo_mode=args.halo_mode)
     t0 = time.time()
-    shm = None
-    if getattr(args, "share_hierarchy", False):
-        # rank 0 builds the hierarchy once and publishes it as files; the others map it read-only (host/share.cpp).
-        # Needed beyond 256^3: at 512^3 eight private copies (8 x 35 GB) do not fit in the box's RAM.
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        shm = os.path.join(base, f"sparsh_hier_{os.environ.get('MASTER_PORT', '0')}_{grid}")
-        A = amg = None
-        if rank == 0:
-            host.set_options(threads=os.cpu_count() or 1)  # the other ranks are waiting: all cores to the one setup
-            A = host.HostMatrix.poisson3d(grid, grid, grid)
-            amg = host.HostAmg(A)
-            amg.save(shm)
-            host.set_options(threads=threads)
-            amg.free()  # rank 0 drops its private copy too: one copy of the hierarchy per node, in the page cache
-            A.free()
-            A = None
-        dist.barrier()
-        amg = host.HostAmg.load(shm)
-    else:
-        A = host.HostMatrix.poisson3d(grid, grid, grid)
-        amg = host.HostAmg(A)  # every rank builds the (sequential) host hierarchy, keeps only its part on the GPU
+    A, amg, shm = host_hierarchy(grid, rank, threads, getattr(args, "share_hierarchy", False), dist.barrier)
     t_setup = time.time() - t0
     plan = DistPlan(amg, world, rank, tail_threshold=args.tail_threshold)
     dH = plan.upload()
@@ -281,14 +293,7 @@ def bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED):
             rr = rr.cpu().numpy()
             m = rr >= 0
             x_full[rr[m]] = xr.cpu().numpy()[m]
-        if A is not None:
-            Ax = A.times(x_full)
-        else:  # shared hierarchy: level 0 lives in the mapped files
-            import scipy.sparse as sps
-
-            L0 = amg.levels()[0]["A"]
-            Ax = sps.csr_matrix((L0.val, L0.colindex, L0.rowptr), shape=(n, n)) @ x_full
-        r_true = float(np.linalg.norm(np.ones(n) - Ax))
+        r_true = float(np.linalg.norm(np.ones(n) - level0_times(A, amg, x_full)))
         # roofline of the dominant kernel on this rank's block of the finest level (interior rows of a Jacobi sweep)
         peak, peak_kind = measured_peak()
         line = {"metric": METRIC, "value": solve_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,

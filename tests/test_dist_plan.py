@@ -22,6 +22,18 @@ def test_partition_plans_with_gloo(world, shape, coarsening):
     assert "DIST_PLAN_OK" in out.stdout
 
 
+def test_shared_hierarchy_under_gloo():
+    """bench.py --gpus N --share-hierarchy, the host part: rank 0 builds and publishes, every rank (0 included) maps the
+    same copy, cuts its plan out of it, and rank 0 can still form A x for the residual check (world size 2, gloo)."""
+    port = 29500 + (os.getpid() % 2000) + 31
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "share_cpu_worker.py"), "20"]
+    env = dict(os.environ, OMP_NUM_THREADS="2", CUDA_VISIBLE_DEVICES="", MASTER_PORT=str(port))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
 def test_local_blocks_keep_the_compressed_formats():
     """The [owned | halo] relabelling of a slab partition shifts all halo columns of a block by one constant, so the
     local blocks of a stencil hierarchy still qualify for csr-dict16 and csr-pattern8 (no escape rows)."""
