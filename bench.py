@@ -233,6 +233,9 @@ def run_ours(args):
     e2e_s = max(e0.elapsed_time(e1) * 1e-3 / args.steps, e2e_wall)  # wall clock covers the host-side orchestration too
     clocks = sampler.stop()
     x_final = x_host.copy()
+    if args.dump_hist:  # residual history of the solve, for the pin against the reference's own history (tools/)
+        json.dump({"grid": grid, "iterations": int(it), "tol": tol, "history": [float(v) for v in hist]},
+                  open(args.dump_hist, "w"))
 
     # roofline of the dominant kernel: fused Jacobi sweep on the finest level, timed alone on the same stream
     A0, _, _ = dH.level(0)
@@ -325,6 +328,7 @@ def main():
     ap.add_argument("--share-hierarchy", action="store_true",
                     help="N>1: rank 0 builds the host hierarchy once, the other ranks map it (needed beyond 256^3)")
     ap.add_argument("--halo-mode", type=int, default=1, help="N>1: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv")
+    ap.add_argument("--dump-hist", default=None, help="N=1: write the PCG residual history of the solve to this JSON file")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: honour --warmup/--max-iter literally, do not insist on convergence")
     args = ap.parse_args()

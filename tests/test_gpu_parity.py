@@ -153,11 +153,6 @@ def test_dict_format_is_bit_identical(sp, oracle, coarsening, threads):
     assert used >= 2
 
 
-# csr-pattern8 has not had its B200 parity + timing runs yet: it stays opt-in (SPARSH_PATTERN) and so do its tests
-PATTERN_TESTS = os.environ.get("SPARSH_TEST_PATTERN", "0") == "1"
-
-
-@pytest.mark.skipif(not PATTERN_TESTS, reason="opt-in: SPARSH_TEST_PATTERN=1 (csr-pattern8 is experimental)")
 @pytest.mark.parametrize("coarsening", [0, 1])
 @pytest.mark.parametrize("threads", [128, 256])
 def test_pattern_format_is_bit_identical(sp, oracle, coarsening, threads, monkeypatch):
@@ -202,7 +197,6 @@ def test_pattern_format_is_bit_identical(sp, oracle, coarsening, threads, monkey
     assert used >= 3
 
 
-@pytest.mark.skipif(not PATTERN_TESTS, reason="opt-in: SPARSH_TEST_PATTERN=1 (csr-pattern8 is experimental)")
 def test_pattern_format_solver_history(sp, oracle, monkeypatch):
     """whole AMG-PCG solve with the pattern kernel on every level that has the twin: same history as the oracle"""
     monkeypatch.setenv("SPARSH_PATTERN", "1")
@@ -224,8 +218,6 @@ def test_pattern_format_solver_history(sp, oracle, monkeypatch):
     np.testing.assert_array_equal(dx.download(), dx0.download())  # same bits as the default kernels
 
 
-@pytest.mark.skipif(os.environ.get("SPARSH_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: SPARSH_TEST_EXPERIMENTAL=1 (smoothed aggregation has not had its first GPU run)")
 def test_smoothed_aggregation_hierarchy_on_gpu(sp, oracle):
     """a smoothed-aggregation hierarchy (general P, 30-60 nnz/row coarse operators) through the same
     device path: V-cycle and AMG-PCG histories against the oracle running the same hierarchy."""
@@ -260,8 +252,6 @@ def test_smoothed_aggregation_hierarchy_on_gpu(sp, oracle):
     assert_hist(hist[:m], hist_ref[:m])
 
 
-@pytest.mark.skipif(os.environ.get("SPARSH_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: SPARSH_TEST_EXPERIMENTAL=1 (GMRES has not had its first GPU run)")
 def test_gmres_matches_the_oracle_statement(sp, oracle, fixture_system):
     """restarted GMRES (CGS2 + Givens) on the device against the oracle's statement of the same algorithm:
     plain on a nonsymmetric matrix (full and restarted), V-cycle-preconditioned on the bundled system."""
