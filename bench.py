@@ -34,22 +34,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# PCG iterations to rel 1e-8 on 3D Poisson n^3, b = 1, HEM hierarchy, V(7,7): measured by this repo's solver on a B200
-# (profiles/); by parity the reference needs the same count (+-1).  Used ONLY to extrapolate bounded CPU samples.
-EXPECTED_PCG_ITERS = {}
-_iters_file = os.path.join(ROOT, "profiles", "pcg_iterations.json")
-if os.path.exists(_iters_file):
-    EXPECTED_PCG_ITERS = {int(k): int(v) for k, v in json.load(open(_iters_file)).items()}
+# PCG iterations to rel 1e-8 on 3D Poisson n^3, b = 1, HEM hierarchy, V(7,7): the count the REFERENCE ITSELF needs (its
+# stock Solver_PCG_1 run to convergence by tools/pin_reference_pcg.py, frozen under tests/golden/); the GPU path's count
+# is gated against it by tests/test_gpu_host_api.py.  Used only when the reference arm is asked to skip its own
+# converged solve (--warmup 0).
+def reference_iterations(grid):
+    f = os.path.join(ROOT, "tests", "golden", f"pcg_poisson3d_{grid}_ref.json")
+    return int(json.load(open(f))["iterations"]) if os.path.exists(f) else None
+
 
 METRIC = "amg_pcg_solve_seconds_poisson3d_256"
 UNIT = "s"
 
 
 def measured_peak():
-    try:
-        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
-    except Exception:
-        return 6650.0, "fallback"
+    from sparsh_amg_b200 import benchutil
+
+    return benchutil.measured_peak()
 
 
 class ClockSampler:
@@ -93,52 +94,71 @@ def problem_rhs(n):
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(grid, iters_per_sample, samples, warm, threads):
-    """returns (seconds per PCG iteration, setup seconds, history) using oracle/_ref (the reference's own sources)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_bindings import CSR, Oracle, Ref, RefAmg, have_ref
+class CpuReference:
+    """the reference's own host code (oracle/_ref: its sources compiled unmodified against the OpenMP MKL shim) on one
+    n^3 Poisson system: its setup (AMG_solver::AMG_solver_setup_jacobi, HEM as shipped) runs once in the constructor"""
 
-    if not have_ref():
-        raise RuntimeError("oracle/_ref/libsparsh_ref.so missing (built where /root/reference exists)")
-    o = Oracle.get()
-    o.set_threads(threads)
-    r = Ref.get()
-    r.set_threads(threads)
-    A = o.gen_poisson3d(grid, grid, grid)
-    ref = RefAmg(A)  # AMG_solver::AMG_solver_setup_jacobi, unmodified, HEM as shipped
-    b = problem_rhs(A.nrow)
-    times = []
-    hist = None
-    for s in range(warm + samples):
-        t, _, hist = ref.pcg_sample(b, np.zeros(A.nrow), iters_per_sample)
-        if s >= warm:
-            times.append(t / iters_per_sample)
-    return float(np.mean(times)), ref.setup_seconds, hist, ref.nlevels
+    def __init__(self, grid, threads):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_bindings import Oracle, Ref, RefAmg, have_ref
+
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libsparsh_ref.so missing (built where /root/reference exists)")
+        o = Oracle.get()
+        o.set_threads(threads)
+        Ref.get().set_threads(threads)
+        self.A = o.gen_poisson3d(grid, grid, grid)
+        self.ref = RefAmg(self.A)
+        self.b = problem_rhs(self.A.nrow)
+        self.threads = threads
+
+    def sample(self, iters):
+        """seconds per iteration of a bounded sample: `iters` iterations of Solver_PCG_1's loop"""
+        t, _, _ = self.ref.pcg_sample(self.b, np.zeros(self.A.nrow), iters)
+        return t / iters
+
+    def converged(self, max_iter=500):
+        """one solve to rel 1e-8 with the reference's own stopping rule -> (seconds, iterations, history)"""
+        t, _, hist = self.ref.pcg_solve(self.b, np.zeros(self.A.nrow), 1e-8 * float(np.linalg.norm(self.b)), max_iter)
+        return t, len(hist) - 1, hist
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # under torchrun only rank 0 runs the CPU arm
+    from sparsh_amg_b200 import benchutil
+
     threads = os.cpu_count() or 1
     grid = args.grid
-    per_iter, setup_s, hist, nlev = cpu_reference_sample(grid, args.ref_iters, args.steps, min(args.warmup, 1), threads)
-    iters = EXPECTED_PCG_ITERS.get(grid)
-    sample = (f"{args.steps} samples x {args.ref_iters} PCG iterations of the full {grid}^3 system (reference "
-              f"Solver_PCG_1 loop body + its own AMG_solve_jacobi V(7,7) cycle, unmodified sources, OpenMP MKL shim), "
-              f"{threads} threads")
+    cpu = CpuReference(grid, threads)
+    nlev = cpu.ref.nlevels
+    conv = None
+    iters = reference_iterations(grid)
+    if args.warmup >= 1:  # warm-up = ONE solve run to convergence: measured iteration count and measured solve seconds
+        t_full, iters, hist = cpu.converged()
+        conv = {"seconds": t_full, "iterations": iters, "final_rel_residual": float(hist[-1] / hist[0])}
+    per_iter = float(np.mean([cpu.sample(args.ref_iters) for _ in range(args.steps)]))
+    sample = (f"{args.steps} steps, each a bounded sample of {args.ref_iters} PCG iterations of the full {grid}^3 system "
+              f"(the loop body of the reference's Solver_PCG_1, src/AMG_main_solvers.cpp:136-152, around its own "
+              f"AMG_solve_jacobi V(7,7) cycle; unmodified sources + OpenMP MKL shim), {threads} threads")
     if iters:
         value = per_iter * iters
-        sample += f"; solve seconds = seconds/iteration x {iters} iterations (the count this config needs to rel 1e-8)"
+        sample += (f"; value = mean seconds/iteration x {iters} iterations"
+                   + (" (the count the converged warm-up solve of this run needed)" if conv else
+                      " (the count the reference's stock Solver_PCG_1 needs, tests/golden)"))
     else:
         value = per_iter
         sample += "; iteration count to rel 1e-8 unknown here: value is seconds per PCG ITERATION"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"AMG-PCG, 3D 7-point Poisson {grid}^3, HEM hierarchy ({nlev} levels), V(7,7) "
-                                   f"Jacobi, rel tol 1e-8, b=1, x0=0", "grid": grid,
-                       "seconds_per_pcg_iteration": per_iter, "reference_setup_seconds": setup_s},
+            "config": {"workload": benchutil.workload(grid, nlev), "grid": grid, "rows": int(cpu.A.nrow),
+                       "nnz": int(cpu.A.nnz)},
+            "details": {"seconds_per_pcg_iteration": per_iter, "reference_setup_seconds": cpu.ref.setup_seconds,
+                        "converged_solve": conv, "extrapolated": True,
+                        "driver": "oracle/ref_harness.cpp: ref_pcg_sample / ref_pcg_solve (Solver_PCG_1's loop on a "
+                                  "hierarchy built once by the reference's AMG_solver_setup_jacobi)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -160,7 +180,7 @@ def run_ours(args):
     if world > 1:
         from sparsh_amg_b200 import distributed as dist_mod
 
-        return dist_mod.bench_main(args, METRIC, UNIT, ClockSampler, measured_peak, EXPECTED_PCG_ITERS)
+        return dist_mod.bench_main(args, METRIC, UNIT, ClockSampler)
 
     torch.cuda.set_device(local_rank)
     sp.init(local_rank)
@@ -237,31 +257,29 @@ def run_ours(args):
         json.dump({"grid": grid, "iterations": int(it), "tol": tol, "history": [float(v) for v in hist]},
                   open(args.dump_hist, "w"))
 
-    # roofline of the dominant kernel: fused Jacobi sweep on the finest level, timed alone on the same stream
+    # roofline of the dominant kernel (fused Jacobi sweep on the finest level), timed alone on the same stream: the
+    # kernel the solve really runs, then the same matrix forced to plain CSR (the kernel north_star's ">= 70 % of HBM
+    # peak" is written for), then every other kernel of the iteration
+    from sparsh_amg_b200 import benchutil
+
     A0, _, _ = dH.level(0)
     z = A0.nnz
     kind, tl, _ = A0.kernel()
-    dict_fmt = kind == sp.capi.KIND_DICT
-    pat_fmt = kind == sp.capi.KIND_PATTERN  # opt-in (SPARSH_PATTERN=1)
-    jac_bytes = 12 * z + 4 * (n + 1) + 32 * n          # ALGORITHMIC bytes of the CSR operation
-    jac_stored = (2 if dict_fmt else 12) * z + 4 * (n + 1) + 32 * n  # bytes the kernel actually has to move
-    if pat_fmt:
-        jac_stored = 25 * n  # pattern byte + b + x + x' per row; the diagonal comes from the pattern table
     tb = sp.DeviceVector(n)
-    reps = 20
-    lib.sparsh_jacobi(A0.h, db.ptr, dx.ptr, tb.ptr, 0.66667, 4)
-    j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    j0.record(stream)
-    lib.sparsh_jacobi(A0.h, db.ptr, dx.ptr, tb.ptr, 0.66667, reps)
-    j1.record(stream)
-    j1.synchronize()
-    jac_s = j0.elapsed_time(j1) * 1e-3 / reps
-    peak, peak_kind = measured_peak()
-    achieved = jac_bytes / jac_s / 1e9
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "jacobi_dram_traffic.json")
-    if os.path.exists(tf):
-        traffic = json.load(open(tf)).get(f"{grid}_pattern" if pat_fmt else f"{grid}_dict" if dict_fmt else str(grid))
+    roof, roof_csr, kernels = {"bound": "hbm"}, None, None
+    try:
+        roof = benchutil.roofline_jacobi(torch, stream, lib, A0, db, dx, tb, grid)
+        kernels = benchutil.kernel_table(torch, stream, lib, dH, db, dx, grid)
+        A0.force_kernel(sp.capi.KIND_STREAM, 256)
+        roof_csr = benchutil.roofline_jacobi(torch, stream, lib, A0, db, dx, tb, grid)
+        csr_spmv = benchutil.timed(torch, stream, lambda: sp.capi.check(lib.sparsh_spmv(A0.h, dx.ptr, tb.ptr)), 20)
+        nb = benchutil.csr_bytes("spmv", n, n, z)
+        roof_csr["spmv"] = {"kernel": "csr_stream_kernel<256,EPI_SPMV>", "ms_per_launch": csr_spmv * 1e3, "bytes_per_launch": nb,
+                            "achieved": nb / csr_spmv / 1e9, "frac": nb / csr_spmv / 1e9 / roof_csr["peak"],
+                            "frac_of_8TBs_nominal": nb / csr_spmv / 1e9 / 8000.0}
+        A0.force_kernel(kind, tl)
+    except Exception as e:  # the solve timing above must survive a failure of the reporting extras
+        roof["error"] = f"{type(e).__name__}: {e}"
     vbytes = dH.vcycle_bytes(True)
     iter_bytes = vbytes + (12 * z + 4 * (n + 1) + 16 * n) + 48 * n + 16 * n + 24 * n  # + SpMV, x/r update, dot, p update
 
@@ -271,11 +289,13 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            per_iter, setup_s, _, _ = cpu_reference_sample(grid, args.ref_iters, 1, 0, threads)
+            ref = CpuReference(grid, threads)
+            per_iter = ref.sample(args.ref_iters)
             cpu = {"value": per_iter * it, "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": f"{args.ref_iters} PCG iterations of the full {grid}^3 system by the reference's own host "
                              f"code (oracle/_ref: unmodified sources + OpenMP MKL shim), seconds/iteration x {it} "
-                             f"iterations; reference setup {setup_s:.1f}s not included",
+                             f"iterations (the reference needs the same {reference_iterations(grid)}: tests/golden); "
+                             f"reference setup {ref.ref.setup_seconds:.1f}s not included",
                    "seconds_per_pcg_iteration": per_iter}
         except Exception as e:  # the checker is optional for the measurement itself
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"unavailable: {e}"}
@@ -283,32 +303,20 @@ def run_ours(args):
     line = {"metric": METRIC, "value": solve_s, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": solve_s * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"AMG-PCG, 3D 7-point Poisson {grid}^3, HEM hierarchy ({amg.nlevels} levels), "
-                                   f"V(7,7) Jacobi, rel tol 1e-8, b=1, x0=0", "grid": grid, "rows": n, "nnz": z,
-                       "pcg_iterations": it, "final_rel_residual": float(hist[-1] / hist[0]),
-                       "true_rel_residual": r_true / float(np.linalg.norm(b_host)),
-                       "ms_per_pcg_iteration": solve_s * 1e3 / max(it, 1),
-                       "iteration_algorithmic_gb": iter_bytes / 1e9,
-                       "solve_effective_gbs": iter_bytes * it / solve_s / 1e9,
-                       "l2": "inputs larger than L2 (finest matrix 1.4 GB vs 126 MB)", "cuda_graph": True,
-                       "host_setup_seconds": rep["setup_seconds"], "upload_seconds": rep2["upload_seconds"],
-                       "matrix_generation_seconds": t_gen},
+            "config": {"workload": benchutil.workload(grid, amg.nlevels), "grid": grid, "rows": n, "nnz": z},
+            "details": {"pcg_iterations": it, "reference_pcg_iterations": reference_iterations(grid),
+                        "final_rel_residual": float(hist[-1] / hist[0]),
+                        "true_rel_residual": r_true / float(np.linalg.norm(b_host)),
+                        "ms_per_pcg_iteration": solve_s * 1e3 / max(it, 1),
+                        "iteration_algorithmic_gb": iter_bytes / 1e9,
+                        "solve_effective_gbs": iter_bytes * it / solve_s / 1e9,
+                        "l2": "inputs larger than L2 (finest matrix 1.4 GB vs 126 MB): no flush needed", "cuda_graph": True,
+                        "host_setup_seconds": rep["setup_seconds"], "upload_seconds": rep2["upload_seconds"],
+                        "matrix_generation_seconds": t_gen},
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8,
                     "pcg_iterations": it_h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm",
-                         "kernel": f"{'csr_pattern_kernel' if pat_fmt else 'csr_dict_kernel' if dict_fmt else 'csr_stream_kernel'}<{tl},EPI_JACOBI> "
-                                   "(fused Jacobi sweep, level 0)",
-                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": jac_bytes,
-                         "ms_per_launch": jac_s * 1e3, "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "format": "csr-pattern8 (lossless: 1-byte row pattern id)" if pat_fmt else
-                                   "csr-dict16 (lossless: 16-bit value/offset codes, 2 B/nnz)" if dict_fmt else "csr",
-                         "stored_bytes_per_launch": jac_stored, "stored_gbs": jac_stored / jac_s / 1e9,
-                         "stored_frac": jac_stored / jac_s / 1e9 / peak,
-                         "note": ("achieved counts the ALGORITHMIC CSR bytes (12 B/nnz); the kernel reads the lossless "
-                                  "csr-dict16 twin, so frac > 1 is compression, stored_frac is the DRAM-roofline "
-                                  "fraction of what is really moved") if dict_fmt else ""},
+            "roofline": roof, "roofline_csr": roof_csr, "kernels": kernels,
             "cpu_baseline": cpu, "clocks": clocks}
     print(json.dumps(line), flush=True)
 

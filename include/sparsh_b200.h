@@ -138,6 +138,9 @@ int sparsh_prolong_add(sparsh_matrix_t P, const double *d_xc, double *d_xf);
  * Reductions are two-stage with a fixed tree: bit-reproducible run to run. */
 int sparsh_dot(size_t n, const double *d_x, const double *d_y, double *h_out);
 int sparsh_nrm2(size_t n, const double *d_x, double *h_out);
+/* the same reduction with the result left in DEVICE memory and no host synchronisation (cublasDdot under
+ * CUBLAS_POINTER_MODE_DEVICE; the Krylov drivers use this form internally, src/AMG_main_solvers.cu:357 syncs instead) */
+int sparsh_dot_device(size_t n, const double *d_x, const double *d_y, double *d_out);
 int sparsh_axpy(size_t n, double a, const double *d_x, double *d_y);                 /* y += a x          */
 int sparsh_axpby(size_t n, double a, const double *d_x, double b, double *d_y);      /* y = a x + b y     */
 int sparsh_axpbypcz(size_t n, double a, const double *d_x, double b, const double *d_y, double c,

@@ -285,7 +285,9 @@ void ref_spmv(void *hv, int lvl, const double *x, double *y) {
 // the bounded CPU sample of bench.py.  The preconditioner is the reference's own AMG_solve_jacobi(r,z,1);
 // SpMV/BLAS-1 go through the same shim entry points the reference calls.  Returns seconds for the m
 // iterations (the initial residual + first preconditioner call, :124-134, are outside the timed region).
-double ref_pcg_sample(void *hv, const double *b, double *x, int m, double *hist) {
+// tol < 0: exactly m iterations (bounded sample).  tol >= 0: the reference's own stopping rule, `count++ < nrow && r1 > tol`
+// (:136), capped at m; *iters receives the number of iterations done.
+static double ref_pcg_run(void *hv, const double *b, double *x, int m, double tol, double *hist, int *iters) {
     CoutCapture cap;
     RefAmg *h = (RefAmg *)hv;
     sp_matrix_mg &A = *h->A;
@@ -296,10 +298,13 @@ double ref_pcg_sample(void *hv, const double *b, double *x, int m, double *hist)
     cblas_daxpby(n, 1.0, b, 1, -1.0, r0, 1);
     double r1 = cblas_dnrm2(n, r0, 1);
     if (hist) hist[0] = r1;
+    std::fill(z0, z0 + n, 0);  // the reference leaves z0 uninitialised here
     h->S->AMG_solve_jacobi(r0, z0, 1);
     std::copy(z0, z0 + n, p);
     double t0 = omp_get_wtime();
-    for (int it = 1; it <= m; it++) {
+    int it = 0;
+    while (it < m && (tol < 0.0 || r1 > tol)) {
+        it++;
         mkl_sparse_d_mv(SPARSE_OPERATION_NON_TRANSPOSE, 1.0, A.A1, A.des, p, 0.0, Ap);
         double alpha = cblas_ddot(n, p, 1, Ap, 1);
         double s = cblas_ddot(n, r0, 1, z0, 1);
@@ -314,11 +319,19 @@ double ref_pcg_sample(void *hv, const double *b, double *x, int m, double *hist)
         if (hist) hist[it] = r1;
     }
     double t = omp_get_wtime() - t0;
+    if (iters) *iters = it;
     delete[] Ap;
     delete[] p;
     delete[] z0;
     delete[] r0;
     return t;
+}
+double ref_pcg_sample(void *hv, const double *b, double *x, int m, double *hist) {
+    return ref_pcg_run(hv, b, x, m, -1.0, hist, nullptr);
+}
+// the same loop run to convergence (||r|| <= tol, at most max_iter iterations): bench.py's converged reference solve
+double ref_pcg_solve(void *hv, const double *b, double *x, double tol, int max_iter, double *hist, int *iters) {
+    return ref_pcg_run(hv, b, x, max_iter, tol, hist, iters);
 }
 
 // Whole reference solvers by name, history captured from their own prints.  x is in/out.

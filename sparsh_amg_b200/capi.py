@@ -74,6 +74,7 @@ SIGNATURES = {
     "sparsh_prolong_add": (_i, [_vp, _vp, _vp]),
     "sparsh_dot": (_i, [_sz, _vp, _vp, c_dbl_p]),
     "sparsh_nrm2": (_i, [_sz, _vp, c_dbl_p]),
+    "sparsh_dot_device": (_i, [_sz, _vp, _vp, _vp]),
     "sparsh_axpy": (_i, [_sz, _d, _vp, _vp]),
     "sparsh_axpby": (_i, [_sz, _d, _vp, _d, _vp]),
     "sparsh_axpbypcz": (_i, [_sz, _d, _vp, _d, _vp, _d, _vp]),

@@ -161,6 +161,11 @@ int sparsh_dot(size_t n, const double *d_x, const double *d_y, double *h_out) {
     SP_TRY(k_dot(n, d_x, d_y, ctx().d_scalar));
     return fetch_scalar(0, h_out);
 }
+int sparsh_dot_device(size_t n, const double *d_x, const double *d_y, double *d_out) {
+    SP_TRY(ensure_init());
+    SP_REQUIRE(d_out != nullptr, "d_out is NULL");
+    return k_dot(n, d_x, d_y, d_out);
+}
 int sparsh_nrm2(size_t n, const double *d_x, double *h_out) {
     SP_TRY(ensure_init());
     SP_TRY(k_dot(n, d_x, d_x, ctx().d_scalar));

@@ -371,6 +371,8 @@ class Ref:
         lib.ref_spmv.argtypes = [C.c_void_p, C.c_int, c_dbl_p, c_dbl_p]
         lib.ref_pcg_sample.restype = C.c_double
         lib.ref_pcg_sample.argtypes = [C.c_void_p, c_dbl_p, c_dbl_p, C.c_int, c_dbl_p]
+        lib.ref_pcg_solve.restype = C.c_double
+        lib.ref_pcg_solve.argtypes = [C.c_void_p, c_dbl_p, c_dbl_p, C.c_double, C.c_int, c_dbl_p, c_int_p]
         lib.ref_solve.argtypes = [C.c_char_p, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
                                   C.c_int]
 
@@ -504,3 +506,11 @@ class RefAmg:
         hist = np.zeros(m + 1)
         t = self.r.lib.ref_pcg_sample(self.h, dp(b), dp(x), m, dp(hist))
         return t, x, hist
+
+    def pcg_solve(self, b, x, tol, max_iter=500):
+        """Solver_PCG_1's loop run to ||r|| <= tol on this hierarchy -> (seconds, x, history incl. the initial residual)"""
+        x = x.copy()
+        hist = np.zeros(max_iter + 1)
+        it = C.c_int()
+        t = self.r.lib.ref_pcg_solve(self.h, dp(b), dp(x), float(tol), int(max_iter), dp(hist), C.byref(it))
+        return t, x, hist[: it.value + 1]

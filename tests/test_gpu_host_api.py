@@ -90,8 +90,37 @@ def test_relative_tolerance_mode_and_beck(host, oracle):
     M.free()
 
 
+def reference_pcg_golden(grid):
+    """history of the reference's own stock Solver_PCG_1 at full size (tools/pin_reference_pcg.py, run where
+    /root/reference exists; the reference prints ||r|| after each iteration only)"""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"pcg_poisson3d_{grid}_ref.json")))
+    return g["iterations"], np.array([g["initial_residual"]] + g["history_after_iteration"])
+
+
+def test_pcg_history_128_matches_the_reference_solver(host):
+    """3D Poisson 128^3 (2.1M rows, 11 levels): iteration count and residual history of the reference's Solver_PCG_1"""
+    import sparsh_amg_b200 as sp
+
+    want_it, want = reference_pcg_golden(128)
+    A = host.HostMatrix.poisson3d(128, 128, 128)
+    amg = host.HostAmg(A)
+    dH = amg.upload()
+    n = A.nrow
+    db, dx = sp.DeviceVector(data=np.ones(n)), sp.DeviceVector(n).fill(0.0)
+    it, hist, ok = dH.pcg(db, dx, 1e-8 * np.sqrt(n), 1000)
+    assert ok and it == want_it
+    assert_hist(hist, want)
+    amg.free()
+    A.free()
+
+
 def test_full_size_properties_256(host):
-    """BASELINE config 3 at full size (16.8M rows): convergence to rel 1e-8, true residual, determinism."""
+    """BASELINE config 3 at full size (16.8M rows): the reference's own iteration count and residual history (its
+    stock Solver_PCG_1 run to convergence at 256^3, frozen in tests/golden/), convergence to rel 1e-8, true residual,
+    determinism."""
     import sparsh_amg_b200 as sp
 
     host.set_options(threads=32)
@@ -105,6 +134,9 @@ def test_full_size_properties_256(host):
     tol = 1e-8 * np.sqrt(n)
     it, hist, ok = dH.pcg(db, dx, tol, 1000)
     assert ok and hist[-1] <= tol
+    want_it, want = reference_pcg_golden(256)
+    assert it == want_it == 30                       # north_star: same iteration count as the reference
+    assert_hist(hist, want)                          # and its history to 1e-10 relative
     x = dx.download()
     r = b - A.times(x)
     assert np.linalg.norm(r) <= 1.05 * tol          # recurrence residual == true residual

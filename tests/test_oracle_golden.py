@@ -225,3 +225,19 @@ def test_gmres_restatement_against_scipy(oracle, fixture_system):
     assert np.linalg.norm(fb - F.to_scipy() @ xp) <= 1e-8 * (1 + 1e-6)
     _, hpcg = amg.pcg(fb, np.zeros(F.nrow), 1e-8)
     assert len(hp) - 1 <= len(hpcg) - 1 + 2  # GMRES minimises the residual: no worse than PCG (+restart slack)
+
+
+def test_oracle_pcg_128_matches_the_reference_solver(oracle):
+    """the C restatement against the reference's stock Solver_PCG_1 at 128^3 (2.1M rows, 11 levels): iteration count and
+    residual history frozen by tools/pin_reference_pcg.py (the 256^3 twin of this golden gates the GPU path at full size)"""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pcg_poisson3d_128_ref.json")))
+    A = oracle.gen_poisson3d(128, 128, 128)
+    assert (A.nrow, A.nnz) == (g["rows"], g["nnz"])
+    b = np.ones(A.nrow)
+    _, hist = OracleAmg(A).pcg(b, np.zeros(A.nrow), g["tol_abs"])
+    assert len(hist) - 1 == g["iterations"]
+    np.testing.assert_allclose(hist[0], g["initial_residual"], rtol=1e-15)
+    np.testing.assert_allclose(hist[1:], g["history_after_iteration"], rtol=1e-10, atol=1e-13 * hist[0])
