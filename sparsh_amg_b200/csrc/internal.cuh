@@ -107,6 +107,20 @@ struct PatWindows {
     int w0;                                 // window that contains offset 0 (-1: none)
     const unsigned char *__restrict__ win;  // n_ent
 };
+// Pattern 0 (the most frequent row: patterns are numbered by decreasing row count) travels BY VALUE in the kernel
+// parameters, so the lean kernel reads its offsets and values as constant-bank operands: no shared-memory look-up, no
+// register, and — because the offsets do not depend on anything loaded — every gather of a row can be issued before
+// the row's pattern byte has arrived (csr_pat2_kernel in spmv.cu).
+constexpr int PAT0_MAX = 32;
+struct Pat0 {
+    int len = 0;      // entries of pattern 0 (0: the lean kernel does not apply)
+    int kdiag = -1;   // index of its offset-0 entry (-1: none)
+    int lo = 0, hi = 0;  // smallest / largest offset
+    double diag = 0.0;   // the tabulated diagonal (pdiag[0])
+    double cover = 0.0;  // fraction of the rows that carry pattern 0
+    int off[PAT0_MAX] = {};
+    double val[PAT0_MAX] = {};
+};
 constexpr int PAT_ESCAPE = 255;    // pattern id of an escape row
 constexpr int PAT_MAX_ENT = 2048;  // table entries over all patterns (32 KB)
 constexpr int PAT_MAX_ROW = 64;    // longer rows are never tabulated
@@ -147,6 +161,7 @@ struct sparsh_matrix_s {
     double *pat_diag = nullptr;
     int n_pat = 0, n_pent = 0, n_escape = 0, pat_far = 0;
     bool has_pat = false;
+    sparsh::Pat0 pat0;                    // len == 0: the lean (speculative-gather) variant does not apply
     sparsh::PatWindows pat_windows = {};  // nwin == 0: the TMA-staged variant does not apply
     unsigned char *pat_win = nullptr;
     sparsh::PatView pattern(bool use_pdiag) const {

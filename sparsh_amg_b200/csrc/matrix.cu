@@ -385,6 +385,26 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     A->n_escape = T.n_escape;
     A->pat_far = 0;
     for (int k = 0; k < n_ent; k++) A->pat_far = std::max(A->pat_far, T.off[k]);
+    {  // pattern 0 by value for the lean kernel (spmv.cu: csr_pat2_kernel)
+        Pat0 z;
+        const int len0 = T.start[1] - T.start[0];
+        long long rows0 = 0;
+        for (int i = 0; i < n; i++) rows0 += pat[i] == 0;
+        if (len0 >= 1 && len0 <= PAT0_MAX) {
+            z.len = len0;
+            z.diag = T.diag[0];
+            z.cover = (double)rows0 / (double)n;
+            z.lo = z.hi = T.off[0];
+            for (int k = 0; k < len0; k++) {
+                z.off[k] = T.off[k];
+                z.val[k] = T.val[k];
+                z.lo = std::min(z.lo, T.off[k]);
+                z.hi = std::max(z.hi, T.off[k]);
+                if (T.off[k] == 0 && z.kdiag < 0) z.kdiag = k;
+            }
+        }
+        A->pat0 = z;
+    }
     {  // x windows for the TMA-staged variant
         PatWindows W = {};
         std::vector<unsigned char> win;
