@@ -14,9 +14,16 @@
 //     when done (fused compute + communication over peer memory).  Sequence counters live in device memory, so all of
 //     it replays inside a CUDA graph: no NCCL call, host round trip or staging copy sits on the exchange path;
 //   * halo_mode 0: pack kernel -> grouped ncclSend/ncclRecv into the halo tail on a communication stream (fallback);
-//   * Krylov scalars: local fixed-tree partial -> ncclAllReduce(sum) of 1-2 doubles, in place in device memory;
-//   * small levels: gathered once per cycle with ncclAllGather and solved redundantly on every GPU by the single-GPU
+//     Boundary strips and interior rows are ONE launch: the strip CTAs carry the lowest block indices (scheduled first),
+//     wait for the flags and signal as soon as the last of them is done; the interior CTAs behind them never wait;
+//   * Krylov scalars: local fixed-tree partial, then a one-warp kernel stores it into a slot of every peer's arena,
+//     waits for the peers' slots and adds them in rank order (deterministic, graph-replayable; ~one NVLink round trip).
+//     The handshake error flag rides along, so every rank learns of a failure in the same iteration;
+//   * small levels: every rank stores its part of the restricted right-hand side straight into all peers' copy of the
+//     replicated vector (flags + acks as above) and the levels are solved redundantly on every GPU by the single-GPU
 //     hierarchy code (levels whose halo would exceed their interior are latency-bound on a partitioned layout).
+//   In halo_mode 1 no NCCL call is left on the iteration path (NCCL bootstraps the IPC handles at setup); halo_mode 0
+//   keeps ncclSend/ncclRecv + ncclAllReduce + ncclAllGather as the reference point.
 #include <nccl.h>
 
 #include <algorithm>
@@ -88,17 +95,32 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
 __device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// spin until *p >= want; gives up after ~2 s and raises *err so a broken handshake can never hang the GPU
-__device__ __forceinline__ void spin_until(const u64 *p, u64 want, int *err) {
-    const long long t0 = clock64();
+__device__ __forceinline__ long long wall_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want; gives up after timeout_ns of wall clock and raises *err so a broken handshake can never hang
+// the GPU (ranks may legitimately be seconds apart: graph instantiation, lazy module loads, a profiler replay)
+__device__ __forceinline__ void spin_until(const u64 *p, u64 want, int *err, long long timeout_ns) {
+    if (ld_acquire_sys(p) >= want) return;
+    const long long t0 = wall_ns();
     while (ld_acquire_sys(p) < want) {
         if (*reinterpret_cast<volatile int *>(err) != 0) break;
-        if (clock64() - t0 > 1000000000ll) {  // ~0.5 s
+        if (wall_ns() - t0 > timeout_ns) {
             atomicExch(err, 1);
             break;
         }
         __nanosleep(64);
     }
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 struct PushArgs {
@@ -113,12 +135,12 @@ struct PushArgs {
 // segments over NVLink, fence, raise the flags (last block to finish)
 __global__ void __launch_bounds__(256)
     push_kernel(const double *__restrict__ x, const int *__restrict__ send_idx, int total, PushArgs a, u64 *seq,
-                unsigned int *ticket, int *err) {
+                unsigned int *ticket, int *err, long long timeout_ns) {
     __shared__ u64 s_prev;
     if (threadIdx.x == 0) s_prev = *reinterpret_cast<volatile u64 *>(seq);
     __syncthreads();
     const u64 prev = s_prev;
-    if (threadIdx.x < a.nnbr) spin_until(a.ack_local[threadIdx.x], prev, err);
+    if (threadIdx.x < a.nnbr) spin_until(a.ack_local[threadIdx.x], prev, err, timeout_ns);
     __syncthreads();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < total) {
@@ -164,6 +186,109 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restri
     if (i < n) dst[i] = src[rows[i]];
 }
 
+// ---- collectives over peer memory (halo_mode 1): no NCCL kernel on the iteration path -------------------------------
+// Shared block at the same offset of every rank's arena.  Slots are double-buffered by the parity of the sequence number:
+// a rank can be at most one collective ahead of a peer that has not read its slot yet (it needs that peer's NEXT
+// contribution to get any further).
+constexpr int RED_SLOTS = 4;  // up to 3 values + the error flag
+struct CollArea {
+    u64 red_flag[2][MAX_NBR];
+    double red_val[2][MAX_NBR][RED_SLOTS];
+    u64 tail_flag[MAX_NBR];  // "rank r's part of the replicated right-hand side has landed", sequence number
+    u64 tail_ack[MAX_NBR];   // "rank r has finished the replicated levels of cycle k": my copy may be overwritten
+};
+struct PeerTab {
+    int nranks, rank;
+    char *base[MAX_NBR];  // mapped arena of every rank (own arena for `rank`)
+};
+
+// In-place all-reduce (sum) of `count` <= 3 device scalars; one thread per rank.  Every rank stores its values into
+// slot [rank] of every peer, raises that peer's flag, waits for all flags in its own arena and adds the slots in RANK
+// ORDER: every rank computes the same bits.  *err travels in the spare slot: after the call it is set on all ranks
+// if it was set on any, so the host loops of all ranks leave in the same iteration.
+__global__ void __launch_bounds__(32)
+    peer_allreduce_kernel(double *vals, int count, PeerTab tab, size_t coll_off, u64 *seq, int *err, long long timeout_ns) {
+    __shared__ double sv[MAX_NBR][RED_SLOTS];
+    const int t = threadIdx.x;
+    const u64 k = *reinterpret_cast<volatile u64 *>(seq) + 1;
+    const int par = (int)(k & 1);
+    if (t < tab.nranks) {
+        CollArea *dst = reinterpret_cast<CollArea *>(tab.base[t] + coll_off);
+        for (int i = 0; i < count; i++) st_relaxed_sys_f64(&dst->red_val[par][tab.rank][i], vals[i]);
+        st_relaxed_sys_f64(&dst->red_val[par][tab.rank][RED_SLOTS - 1], *reinterpret_cast<volatile int *>(err) ? 1.0 : 0.0);
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[par][tab.rank], k);
+        CollArea *mine = reinterpret_cast<CollArea *>(tab.base[tab.rank] + coll_off);
+        spin_until(&mine->red_flag[par][t], k, err, timeout_ns);
+        for (int i = 0; i < count; i++) sv[t][i] = ld_relaxed_sys_f64(&mine->red_val[par][t][i]);
+        sv[t][RED_SLOTS - 1] = ld_relaxed_sys_f64(&mine->red_val[par][t][RED_SLOTS - 1]);
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int i = 0; i < count; i++) {
+            double acc = 0.0;
+            for (int r = 0; r < tab.nranks; r++) acc = __dadd_rn(acc, sv[r][i]);
+            vals[i] = acc;
+        }
+        bool bad = false;
+        for (int r = 0; r < tab.nranks; r++) bad = bad || sv[r][RED_SLOTS - 1] != 0.0;
+        if (bad) atomicExch(err, 1);
+        *reinterpret_cast<volatile u64 *>(seq) = k;
+    }
+}
+
+// Replicated right-hand side: every rank stores its owned entries (global ids `rows`) into ALL ranks' copy of the
+// vector (own copy included), the last CTA raises the flags and then waits until every rank's part has landed here, so
+// the kernels that follow in the stream see the complete vector.  Before overwriting, every CTA makes sure all ranks
+// have finished the replicated levels of the previous cycle (acks raised by tail_ack_kernel).
+__global__ void __launch_bounds__(256)
+    tail_exchange_kernel(const double *__restrict__ src, const int *__restrict__ rows, int n_own, PeerTab tab, size_t vec_off,
+                         size_t coll_off, u64 *seq, unsigned int *ticket, int *err, long long timeout_ns) {
+    __shared__ u64 s_prev;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_prev = *reinterpret_cast<volatile u64 *>(seq);
+    __syncthreads();
+    const u64 prev = s_prev;
+    CollArea *mine = reinterpret_cast<CollArea *>(tab.base[tab.rank] + coll_off);
+    if (threadIdx.x < tab.nranks) spin_until(&mine->tail_ack[threadIdx.x], prev, err, timeout_ns);
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_own; i += gridDim.x * 256) {
+        const double v = src[i];
+        const int g = rows[i];
+        for (int q = 0; q < tab.nranks; q++) reinterpret_cast<double *>(tab.base[q] + vec_off)[g] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < tab.nranks) {
+            __threadfence_system();
+            CollArea *dst = reinterpret_cast<CollArea *>(tab.base[threadIdx.x] + coll_off);
+            st_release_sys(&dst->tail_flag[tab.rank], prev + 1);
+            spin_until(&mine->tail_flag[threadIdx.x], prev + 1, err, timeout_ns);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<volatile u64 *>(seq) = prev + 1;
+            *ticket = 0u;
+            __threadfence();
+        }
+    }
+}
+// the replicated levels of this cycle are done on this rank: gather the owned entries of the correction and tell every
+// rank that its next right-hand side may overwrite my copy
+__global__ void __launch_bounds__(256)
+    tail_gather_ack_kernel(const double *__restrict__ src, const int *__restrict__ rows, int n, double *dst, PeerTab tab,
+                           size_t coll_off, const u64 *seq) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = src[rows[i]];
+    if (blockIdx.x == 0 && threadIdx.x < tab.nranks) {
+        const u64 k = *reinterpret_cast<const volatile u64 *>(seq);
+        CollArea *peer = reinterpret_cast<CollArea *>(tab.base[threadIdx.x] + coll_off);
+        st_release_sys(&peer->tail_ack[tab.rank], k);
+    }
+}
+
 }  // namespace
 
 struct sparsh_dist_s {
@@ -195,13 +320,25 @@ struct sparsh_dist_s {
     std::vector<int> halo_ready;      // buffer id -> (op id + 1) whose halo slices the producing kernel already pushed, 0 = none
     double **d_pm_tab = nullptr;      // [buffer id][neighbour slot] peer address of my slice (fused Jacobi push)
     int *d_err = nullptr, *h_err = nullptr;
+    // peer-memory collectives (CollArea at byte offset coll_off of every arena)
+    size_t coll_off = 0, tailb_off = 0;
+    u64 *red_seq = nullptr, *tail_seq = nullptr;
+    unsigned int *tail_ticket = nullptr;
+    long long timeout_ns = 10000000000ll;  // SPARSH_HALO_TIMEOUT_MS overrides (default 10 s)
+    bool dead = false;                     // a handshake timed out: flags and counters are out of step for good
 };
 
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int make_op(const sparsh_dist_op_desc &d, int shift, int id, DistOp &op) {
+// halo segments start on a 128-byte boundary of their vector: a cache line never mixes owned entries (which the
+// interior rows of a co-resident CTA may pull into L1) with halo entries (which peers overwrite over NVLink)
+inline int align16(int n) { return (n + 15) & ~15; }
+
+int make_op(const sparsh_dist_op_desc &d, int halo_start, int id, DistOp &op) {
+    const int shift = halo_start - d.ncol_local;
+    SP_REQUIRE(shift >= 0, "halo segment overlaps the owned entries");
     op.id = id;
     op.nrow = d.nrow;
     op.ncol_local = d.ncol_local;
@@ -290,7 +427,8 @@ int peer_push(sparsh_dist_s *h, const DistOp &op, double *x) {
     }
     a.ptr[a.nnbr] = op.send_ptr[a.nnbr];
     const int total = op.send_ptr.back();
-    push_kernel<<<(total + 255) / 256, 256, 0, c.stream>>>(x, op.d_send_idx, total, a, h->seq + op.id, h->ticket + op.id, h->d_err);
+    push_kernel<<<(total + 255) / 256, 256, 0, c.stream>>>(x, op.d_send_idx, total, a, h->seq + op.id, h->ticket + op.id, h->d_err,
+                                                            h->timeout_ns);
     count_launch();
     return SPARSH_OK;
 }
@@ -316,6 +454,8 @@ void halo_sync(sparsh_dist_s *h, const DistOp &op, HaloSync &hs) {
     hs.expect = h->expect + op.id;
     hs.ticket = h->ticket2 + op.id;
     hs.err = h->d_err;
+    hs.halo_begin = op.ncol_local + op.shift;
+    hs.timeout_ns = h->timeout_ns;
 }
 
 // ---- halo_mode 0: NCCL point-to-point on a communication stream -----------------------------------------------------
@@ -345,45 +485,28 @@ int nccl_finish() {
     return SPARSH_OK;
 }
 
-// run `f` with the library's current stream temporarily replaced (launch_csr and friends enqueue on ctx().stream)
-struct StreamSwap {
-    cudaStream_t saved;
-    explicit StreamSwap(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
-    ~StreamSwap() { ctx().stream = saved; }
-};
-int fork_aux() {
-    Comm &m = comm();
-    SP_CUDA(cudaEventRecord(m.ev_ready, ctx().stream));
-    SP_CUDA(cudaStreamWaitEvent(m.comm_stream, m.ev_ready, 0));
-    return SPARSH_OK;
-}
-int join_aux() {
-    Comm &m = comm();
-    SP_CUDA(cudaEventRecord(m.ev_done, m.comm_stream));
-    SP_CUDA(cudaStreamWaitEvent(ctx().stream, m.ev_done, 0));
-    return SPARSH_OK;
-}
-
 // y = epi(op x).  The rows that touch the halo (and, for the fused Jacobi, the rows a neighbour needs) form the two
-// boundary strips; they run on the auxiliary stream — generic push if the halo of x is not already on its way, then ONE
-// kernel that waits for the flags, computes, optionally stores the new values into the neighbours and signals — while
-// the interior rows run concurrently on the main stream.  `push_output`: y is the next input of this same operator.
+// boundary strips, everything else is interior.  Peer mode: a generic push first if the halo of x is not already on
+// its way, then ONE launch — the strip CTAs come first in the grid, wait for the flags, compute, optionally store the
+// new values into the neighbours and signal as soon as the last of them is done, while the interior CTAs of the same
+// grid never wait.  `push_output`: y is the next input of this same operator.
 int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, EpiArgs args, bool push_output = false) {
     if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
-    // (the fused reductions need one grid over all rows, and tiny interiors are not worth a separate launch)
-    // splitting buys overlap of the handshake with the interior rows but costs a second launch and a stream fork/join:
-    // worth it only when the interior kernel is long enough (SPARSH_SPLIT_MIN_ROWS overrides the default)
+    // tiny interiors are not worth a separate range (SPARSH_SPLIT_MIN_ROWS overrides the default)
     static const int split_min = [] {
         const char *e = getenv("SPARSH_SPLIT_MIN_ROWS");
-        return e ? atoi(e) : 4096;
+        return e ? atoi(e) : 1024;
     }();
-    const bool split = !reduces && op.ie - op.ib >= split_min && (op.ib > 0 || op.ie < op.nrow);
+    const bool split = op.ie - op.ib >= split_min && (op.ib > 0 || op.ie < op.nrow);
     if (!h->peer) {
+        // NCCL point-to-point: interior rows overlap the transfer as a separate launch (the fused reductions need one
+        // grid over all rows and are not split)
+        const bool split2 = split && !reduces;
         SP_TRY(nccl_start(op, x));
-        if (split) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
+        if (split2) SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));
         SP_TRY(nccl_finish());
-        if (split) return launch_csr2(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, nullptr);
+        if (split2) return launch_csr2(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, nullptr);
         return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     }
     Comm &m = comm();
@@ -393,14 +516,13 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
     h->halo_ready[bx] = 0;
     HaloSync hs;
     halo_sync(h, op, hs);
-    EpiArgs bargs = args;  // boundary strips may carry the fused push
-    if (push_output && epi == EPI_JACOBI && !op.send_rank.empty()) {
+    if (push_output && epi == EPI_JACOBI && !op.send_rank.empty()) {  // the strips carry the fused push
         const int by = buffer_id(h, y);
         SP_REQUIRE(by >= 0 && h->buf_level[by] >= 0, "fused push into a vector outside the arena");
-        bargs.pm_ptr = op.d_pm_ptr;
-        bargs.pm_nbr = op.d_pm_nbr;
-        bargs.pm_off = op.d_pm_off;
-        bargs.pm_dst = h->d_pm_tab + (size_t)by * MAX_NBR;
+        args.pm_ptr = op.d_pm_ptr;
+        args.pm_nbr = op.d_pm_nbr;
+        args.pm_off = op.d_pm_off;
+        args.pm_dst = h->d_pm_tab + (size_t)by * MAX_NBR;
         hs.nsend = (int)op.send_rank.size();
         for (int s = 0; s < hs.nsend; s++) {
             const int q = op.send_rank[s];
@@ -410,23 +532,32 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
         hs.seq = h->seq + op.id;
         h->halo_ready[by] = op.id + 1;
     }
-    if (!split) {
-        if (need_push) SP_TRY(peer_push(h, op, x));
-        return launch_csr2(op.M, epi, x, y, bargs, 0, op.nrow, 0, 0, &hs);
-    }
-    SP_TRY(fork_aux());
-    {
-        StreamSwap sw(m.comm_stream);
-        if (need_push) SP_TRY(peer_push(h, op, x));
-        SP_TRY(launch_csr2(op.M, epi, x, y, bargs, 0, op.ib, op.ie, op.nrow, &hs));
-    }
-    SP_TRY(launch_csr(op.M, epi, x, y, args, op.ib, op.ie));  // interior rows: no halo entry referenced, nothing to send
-    return join_aux();
+    if (need_push) SP_TRY(peer_push(h, op, x));
+    if (!split) return launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
+    return launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
 }
 
-int allreduce_sum(double *d_vals, int count) {
+PeerTab peer_tab(const sparsh_dist_s *h) {
+    Comm &m = comm();
+    PeerTab t;
+    std::memset(&t, 0, sizeof t);
+    t.nranks = m.nranks;
+    t.rank = m.rank;
+    for (int r = 0; r < m.nranks; r++) t.base[r] = h->peer_base[r];
+    return t;
+}
+
+// in-place sum over the ranks of `count` (<= 3) device scalars
+int allreduce_sum(sparsh_dist_s *h, double *d_vals, int count) {
     Comm &m = comm();
     if (m.nranks == 1) return SPARSH_OK;
+    if (h->peer) {
+        SP_REQUIRE(count >= 1 && count < RED_SLOTS, "peer all-reduce handles up to 3 scalars");
+        peer_allreduce_kernel<<<1, 32, 0, ctx().stream>>>(d_vals, count, peer_tab(h), h->coll_off, h->red_seq, h->d_err, h->timeout_ns);
+        count_launch();
+        SP_CUDA(cudaGetLastError());
+        return SPARSH_OK;
+    }
     SP_NCCL(ncclAllReduce(d_vals, d_vals, (size_t)count, ncclDouble, ncclSum, m.comm, ctx().stream));
     return SPARSH_OK;
 }
@@ -477,8 +608,14 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
         double *bnext = l + 1 < nd ? h->lev[l + 1].bbuf : h->btail_local;
         SP_TRY(apply(h, L.R, EPI_SPMV, L.rbuf, bnext, EpiArgs()));
     }
-    // replicated tail: all-gather the restricted right-hand side, solve redundantly, keep the owned rows
-    if (m.nranks > 1) {
+    // replicated tail: every rank contributes its part of the restricted right-hand side to all copies of the vector,
+    // the levels below are solved redundantly, the owned rows of the correction are kept
+    const int gblocks = std::max(1, std::min((h->n_own_tail0 + 255) / 256, 4 * c.sm_count));
+    if (m.nranks > 1 && h->peer) {
+        tail_exchange_kernel<<<gblocks, 256, 0, c.stream>>>(h->btail_local, h->d_tail_rows, h->n_own_tail0, peer_tab(h), h->tailb_off,
+                                                            h->coll_off, h->tail_seq, h->tail_ticket, h->d_err, h->timeout_ns);
+        count_launch();
+    } else if (m.nranks > 1) {
         SP_CUDA(cudaMemcpyAsync(h->tail_send, h->btail_local, sizeof(double) * (size_t)h->n_own_tail0, cudaMemcpyDeviceToDevice, c.stream));
         SP_NCCL(ncclAllGather(h->tail_send, h->tail_recv, (size_t)h->tail_maxc, ncclDouble, m.comm, c.stream));
         const int tot = h->tail_maxc * m.nranks;
@@ -490,7 +627,11 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
         count_launch();
     }
     SP_TRY(enqueue_vcycle(h->tail, h->tail_b, h->tail_x, true));
-    if (h->n_own_tail0 > 0) {
+    if (m.nranks > 1 && h->peer) {
+        tail_gather_ack_kernel<<<gblocks, 256, 0, c.stream>>>(h->tail_x, h->d_tail_rows, h->n_own_tail0, h->xtail_local, peer_tab(h),
+                                                              h->coll_off, h->tail_seq);
+        count_launch();
+    } else if (h->n_own_tail0 > 0) {
         gather_rows_kernel<<<(h->n_own_tail0 + 255) / 256, 256, 0, c.stream>>>(h->tail_x, h->d_tail_rows, h->n_own_tail0, h->xtail_local);
         count_launch();
     }
@@ -547,9 +688,16 @@ int check_handshake(sparsh_dist_s *h) {
     SP_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
     SP_CUDA(cudaStreamSynchronize(ctx().stream));
     if (*h->h_err) {
-        set_error("multi-GPU halo handshake timed out (a neighbour never signalled)");
+        h->dead = true;
+        set_error("multi-GPU halo handshake timed out (a neighbour never signalled); the distributed handle is unusable");
         return SPARSH_ERR_CUDA;
     }
+    return SPARSH_OK;
+}
+// after a timed-out handshake the sequence counters of the ranks are out of step for good: refuse further work
+int check_alive(const sparsh_dist_s *h) {
+    SP_REQUIRE(h != nullptr, "hierarchy is NULL");
+    SP_REQUIRE(!h->dead, "distributed handle is unusable after a halo-handshake timeout: destroy it and create a new one");
     return SPARSH_OK;
 }
 
@@ -675,33 +823,44 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
     h->peer = h->prm.halo_mode == 1 && m.nranks > 1 && m.nranks <= MAX_NBR;
     h->nops = 3 * nd;
     h->lev.resize(nd);
+    if (const char *e = getenv("SPARSH_HALO_TIMEOUT_MS")) h->timeout_ns = std::max(1ll, atoll(e)) * 1000000ll;
 
     // ---- operators.  Vector space of level l is read by A_l (halo segment right after the owned entries) and by
     //      P_{l-1} (its halo segment sits behind A_l's, so the two exchanges never share memory)
+    //      Every halo segment starts on a 128-byte boundary (align16 doubles).
     for (int l = 0; l < nd; l++) {
         DistLevel &L = h->lev[l];
-        SP_TRY(make_op(lev[l].A, 0, 3 * l + 0, L.A));
+        SP_TRY(make_op(lev[l].A, align16(lev[l].A.ncol_local), 3 * l + 0, L.A));
         SP_TRY(make_push_map(lev[l].A, L.A));
-        SP_TRY(make_op(lev[l].P, l + 1 < nd ? lev[l + 1].A.nhalo : 0, 3 * l + 1, L.P));
-        SP_TRY(make_op(lev[l].R, 0, 3 * l + 2, L.R));
+        // P_l gathers from the level l+1 vector: behind A_{l+1}'s halo segment there (the replicated tail has none)
+        const int pstart = l + 1 < nd ? align16(align16(lev[l + 1].A.ncol_local) + lev[l + 1].A.nhalo) : align16(lev[l].P.ncol_local);
+        SP_TRY(make_op(lev[l].P, pstart, 3 * l + 1, L.P));
+        SP_TRY(make_op(lev[l].R, align16(lev[l].R.ncol_local), 3 * l + 2, L.R));
         L.n = lev[l].A.nrow;
         L.n_next = lev[l].R.nrow;
-        L.xcap = (size_t)L.n + lev[l].A.nhalo + (l > 0 ? lev[l - 1].P.nhalo : 0) + 2;
+        const int astart = align16(L.n);
+        L.xcap = (size_t)(l > 0 ? align16(astart + lev[l].A.nhalo) + lev[l - 1].P.nhalo : astart + lev[l].A.nhalo) + 2;
     }
     h->n_own_tail0 = tail_counts[m.rank];
     SP_REQUIRE(h->n_own_tail0 == h->lev[nd - 1].n_next, "owned rows of the first replicated level disagree with R");
 
     // ---- arena: flags first, then every vector that can be the target of a halo exchange (same ORDER on all ranks)
+    //      [op flags | collective area | replicated right-hand side] sit at the SAME offsets on every rank; the vectors
+    //      behind them have rank-dependent sizes, their offsets are exchanged below
     const size_t flag_bytes = align_up(sizeof(u64) * 2 * (size_t)h->nops * m.nranks, 256);
+    h->coll_off = flag_bytes;
+    h->tailb_off = h->coll_off + align_up(sizeof(CollArea), 256);
+    h->n_tail0 = tail[0].nrow;
+    const size_t fixed_bytes = h->tailb_off + align_up(sizeof(double) * ((size_t)h->n_tail0 + 2), 256);
     std::vector<size_t> want;  // bytes per buffer, in buffer-id order
     for (int l = 0; l < nd; l++) {
-        want.push_back(sizeof(double) * h->lev[l].xcap);                               // tbuf
-        want.push_back(sizeof(double) * ((size_t)h->lev[l].n + lev[l].R.nhalo + 2));   // rbuf
-        if (l > 0) want.push_back(sizeof(double) * h->lev[l].xcap);                    // xbuf
+        want.push_back(sizeof(double) * h->lev[l].xcap);                                         // tbuf
+        want.push_back(sizeof(double) * ((size_t)align16(h->lev[l].n) + lev[l].R.nhalo + 2));    // rbuf
+        if (l > 0) want.push_back(sizeof(double) * h->lev[l].xcap);                              // xbuf
     }
-    want.push_back(sizeof(double) * ((size_t)h->n_own_tail0 + lev[nd - 1].P.nhalo + 2));  // xtail_local
-    for (int i = 0; i < 5; i++) want.push_back(sizeof(double) * h->lev[0].xcap);          // Krylov vectors
-    size_t total = flag_bytes;
+    want.push_back(sizeof(double) * ((size_t)align16(h->n_own_tail0) + lev[nd - 1].P.nhalo + 2));  // xtail_local
+    for (int i = 0; i < 5; i++) want.push_back(sizeof(double) * h->lev[0].xcap);                   // Krylov vectors
+    size_t total = fixed_bytes;
     std::vector<size_t> off(want.size());
     for (size_t i = 0; i < want.size(); i++) {
         off[i] = total;
@@ -725,6 +884,7 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
     }
     h->xtail_local = take(-1);
     for (int i = 0; i < 5; i++) h->kv[i] = take(0);
+    h->tail_b = reinterpret_cast<double *>(h->arena + h->tailb_off);
     h->halo_ready.assign(h->bufs.size(), 0);
     for (int l = 1; l < nd; l++) SP_CUDA(cudaMalloc(&h->lev[l].bbuf, sizeof(double) * ((size_t)h->lev[l].n + 2)));
 
@@ -733,6 +893,12 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
     SP_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)h->nops));
     SP_CUDA(cudaMalloc(&h->ticket2, sizeof(unsigned int) * (size_t)h->nops));
     SP_CUDA(cudaMemset(h->ticket2, 0, sizeof(unsigned int) * (size_t)h->nops));
+    SP_CUDA(cudaMalloc(&h->red_seq, sizeof(u64)));
+    SP_CUDA(cudaMalloc(&h->tail_seq, sizeof(u64)));
+    SP_CUDA(cudaMalloc(&h->tail_ticket, sizeof(unsigned int)));
+    SP_CUDA(cudaMemset(h->red_seq, 0, sizeof(u64)));
+    SP_CUDA(cudaMemset(h->tail_seq, 0, sizeof(u64)));
+    SP_CUDA(cudaMemset(h->tail_ticket, 0, sizeof(unsigned int)));
     SP_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
     SP_CUDA(cudaMallocHost(&h->h_err, sizeof(int)));
     SP_CUDA(cudaMemset(h->seq, 0, sizeof(u64) * (size_t)h->nops));
@@ -830,7 +996,6 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
     sparsh_params tp = h->prm;
     tp.use_graph = 0;  // its launches are captured as part of the enclosing distributed graph
     SP_TRY(sparsh_hierarchy_create(ntail, tail, &tp, &h->tail));
-    h->n_tail0 = tail[0].nrow;
     int maxc = 0, displ = 0, my_displ = 0;
     for (int r = 0; r < m.nranks; r++) {
         maxc = std::max(maxc, tail_counts[r]);
@@ -853,7 +1018,6 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
     SP_CUDA(cudaMalloc(&h->tail_send, sizeof(double) * (size_t)h->tail_maxc));
     SP_CUDA(cudaMemset(h->tail_send, 0, sizeof(double) * (size_t)h->tail_maxc));
     SP_CUDA(cudaMalloc(&h->tail_recv, sizeof(double) * (size_t)h->tail_maxc * m.nranks));
-    SP_CUDA(cudaMalloc(&h->tail_b, sizeof(double) * ((size_t)h->n_tail0 + 2)));
     SP_CUDA(cudaMalloc(&h->tail_x, sizeof(double) * ((size_t)h->n_tail0 + 2)));
     SP_CUDA(cudaMalloc(&h->btail_local, sizeof(double) * ((size_t)h->n_own_tail0 + 2)));
     SP_CUDA(cudaMalloc(&h->d_sc, sizeof(double) * 16));
@@ -884,7 +1048,6 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     cudaFree(h->arena);
     cudaFree(h->tail_send);
     cudaFree(h->tail_recv);
-    cudaFree(h->tail_b);
     cudaFree(h->tail_x);
     cudaFree(h->d_tail_map);
     cudaFree(h->d_tail_rows);
@@ -894,6 +1057,9 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     cudaFree(h->ticket);
     cudaFree(h->ticket2);
     cudaFree(h->d_pm_tab);
+    cudaFree(h->red_seq);
+    cudaFree(h->tail_seq);
+    cudaFree(h->tail_ticket);
     cudaFree(h->d_err);
     cudaFreeHost(h->h_err);
     cudaFree(h->d_sc);
@@ -915,7 +1081,8 @@ int sparsh_dist_level_matrix(sparsh_dist_t h, int level, sparsh_matrix_t *A) {
 }
 
 int sparsh_dist_spmv(sparsh_dist_t h, int level, const double *d_x_local, double *d_y_local) {
-    SP_REQUIRE(h != nullptr && level >= 0 && level < (int)h->lev.size(), "bad level");
+    SP_TRY(check_alive(h));
+    SP_REQUIRE(level >= 0 && level < (int)h->lev.size(), "bad level");
     DistLevel &L = h->lev[level];
     SP_CUDA(cudaMemcpyAsync(L.tbuf, d_x_local, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, ctx().stream));
     SP_TRY(apply(h, L.A, EPI_SPMV, L.tbuf, d_y_local, EpiArgs()));
@@ -923,7 +1090,8 @@ int sparsh_dist_spmv(sparsh_dist_t h, int level, const double *d_x_local, double
 }
 
 int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_local, int cycles, int x_is_zero) {
-    SP_REQUIRE(h != nullptr && cycles >= 0, "bad arguments");
+    SP_TRY(check_alive(h));
+    SP_REQUIRE(cycles >= 0, "bad arguments");
     DistLevel &L0 = h->lev[0];
     double *z = h->kv[1];  // halo-capable staging for the caller's x
     SP_CUDA(cudaMemcpyAsync(z, d_x_local, sizeof(double) * (size_t)L0.n, cudaMemcpyDeviceToDevice, ctx().stream));
@@ -935,7 +1103,7 @@ int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_loc
 // Same arithmetic as cg_impl(precond = true) in krylov.cu (reference src/AMG_main_solvers.cpp:107-167); the three
 // reductions of an iteration are completed by in-place all-reduces of device scalars.
 int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int max_iter, double *hist, int *iters_out) {
-    SP_REQUIRE(h != nullptr, "hierarchy is NULL");
+    SP_TRY(check_alive(h));
     Context &c = ctx();
     DistLevel &L0 = h->lev[0];
     const size_t n = (size_t)L0.n;
@@ -952,11 +1120,11 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
     a.b = b;
     SP_TRY(apply(h, L0.A, EPI_RESID, xs, r, a));
     SP_TRY(k_dot(n, r, r, sc + S_RR));
-    SP_TRY(allreduce_sum(sc + S_RR, 1));
+    SP_TRY(allreduce_sum(h, sc + S_RR, 1));
     SP_TRY(dist_run_graphed(h, r, z, 1, [&]() { return enqueue_dist_vcycle(h, r, z, true); }));
     SP_CUDA(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
     SP_TRY(k_dot(n, r, z, sc + S_RZ));
-    SP_TRY(allreduce_sum(sc + S_RZ, 1));
+    SP_TRY(allreduce_sum(h, sc + S_RZ, 1));
     SP_TRY(read_rr());
     SP_CUDA(cudaStreamSynchronize(c.stream));
     double r1 = std::sqrt(h->h_sc[S_RR]);
@@ -968,12 +1136,12 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
         e.xi = p;
         e.red_out = sc + S_PAP;
         SP_TRY(apply(h, L0.A, EPI_SPMV_DOT, p, Ap, e));
-        SP_TRY(allreduce_sum(sc + S_PAP, 1));
+        SP_TRY(allreduce_sum(h, sc + S_PAP, 1));
         SP_TRY(k_pcg_update_xr(n, p, Ap, xs, r, sc + S_RZ, sc + S_PAP, sc + S_RR));
-        SP_TRY(allreduce_sum(sc + S_RR, 1));
         SP_TRY(enqueue_dist_vcycle(h, r, z, true));
         SP_TRY(k_dot(n, z, r, sc + S_RZNEW));
-        SP_TRY(allreduce_sum(sc + S_RZNEW, 1));
+        // z.r and the ||r||^2 partial left behind by the x/r update travel together (slots S_RZNEW, S_RR are adjacent)
+        SP_TRY(allreduce_sum(h, sc + S_RZNEW, 2));
         SP_TRY(k_pcg_update_p(n, z, p, sc + S_RZNEW, sc + S_RZ));
         SP_TRY(k_scalar_copy(sc + S_RZ, sc + S_RZNEW));
         SP_TRY(read_rr());
@@ -984,8 +1152,9 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
         count++;
         SP_TRY(dist_run_graphed(h, x, b, 10, body));
         SP_CUDA(cudaStreamSynchronize(c.stream));
-        if (h->peer && *h->h_err) {
-            set_error("multi-GPU halo handshake timed out (a neighbour never signalled)");
+        if (h->peer && *h->h_err) {  // the flag rides on the all-reduces: every rank sees it in the same iteration
+            h->dead = true;
+            set_error("multi-GPU halo handshake timed out (a neighbour never signalled); the distributed handle is unusable");
             rc = SPARSH_ERR_CUDA;
             break;
         }

@@ -198,9 +198,11 @@ struct EpiArgs {
 };
 int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
                int row_end);
-// rows [b1,e1) followed by rows [b2,e2) in ONE launch (the two boundary strips of a row block)
+// rows [b1,e1), [b2,e2) and [b3,e3) in ONE launch: the first nblk1 CTAs own range 1, the next nblk2 range 2, the rest
+// range 3.  Multi-GPU: ranges 1 and 2 are the two boundary strips of a row block (their CTAs have the lowest block
+// indices, so they are scheduled first and run the halo handshake), range 3 the interior rows.
 struct RowRange {
-    int b1, e1, b2, e2, nblk1;
+    int b1, e1, b2, e2, b3, e3, nblk1, nblk2;
 };
 // multi-GPU: flag handshake fused into the consuming kernel (dist.cu).  Every CTA waits (acquire, system scope) until
 // each neighbour's halo slice has landed before it gathers x; the last CTA to finish advances the sequence counter and
@@ -220,9 +222,22 @@ struct HaloSync {
     sparsh_u64 *seq = nullptr;
     unsigned int *ticket = nullptr;
     int *err = nullptr;
+    // CTAs [0, nstrip) take part in the handshake and in the fused push (the boundary strips); the CTAs behind them
+    // own interior rows, which reference no halo entry and feed no neighbour: they neither wait nor signal.  Set by
+    // the launcher.
+    int nstrip = 0;
+    // columns >= halo_begin of the gathered vector are halo entries, written by peers over NVLink while this grid may
+    // already be resident: they are loaded through L2 (ld.global.cg), never through the non-coherent path
+    int halo_begin = 0x7fffffff;
+    long long timeout_ns = 10000000000ll;  // a wait that lasts longer raises *err instead of hanging the GPU
 };
-int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
-                int b2, int e2, const HaloSync *hs);
+// rows [b1,e1) + [b2,e2) (strips: handshake CTAs when hs is given) + [b3,e3) (interior) in one launch
+int launch_csr3(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
+                int b2, int e2, int b3, int e3, const HaloSync *hs);
+inline int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
+                       int b2, int e2, const HaloSync *hs) {
+    return launch_csr3(A, epi, x, y, args, b1, e1, b2, e2, 0, 0, hs);
+}
 
 // ---- BLAS-1 (blas1.cu) -------------------------------------------------------------------------------------
 int k_fill(double *x, size_t n, double v);

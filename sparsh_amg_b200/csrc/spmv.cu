@@ -18,219 +18,9 @@
 //  * VECTOR (irregular / long rows): 2..32 lanes per row, shuffle-tree reduction (1e-12 parity, not bit-exact).
 #include <cstdlib>
 
-#include "internal.cuh"
+#include "spmv_common.cuh"
 
 namespace sparsh {
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D TMA bulk copy global -> shared
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SPARSH_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SPARSH_DONE;\n"
-        "bra SPARSH_WAIT;\n"
-        "SPARSH_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// dst/src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Multi-GPU flag handshake fused into the consumer (see HaloSync in internal.cuh, producer side in dist.cu)
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ sparsh_u64 ld_acquire_sys_u64(const sparsh_u64 *p) {
-    sparsh_u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(sparsh_u64 *p, sparsh_u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-struct HaloTurn {
-    sparsh_u64 want, prev;
-};
-__device__ __forceinline__ void spin_ge(const sparsh_u64 *p, sparsh_u64 v, int *err) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(p) < v) {
-        // a broken handshake must never hang the GPU: give up after ~0.5 s, and at once if somebody already did
-        if (*reinterpret_cast<volatile int *>(err) != 0) break;
-        if (clock64() - t0 > 1000000000ll) {
-            atomicExch(err, 1);
-            break;
-        }
-        __nanosleep(32);
-    }
-}
-// called by every thread of the CTA, before the first gather of x; contains a CTA barrier
-__device__ __forceinline__ HaloTurn halo_wait(const HaloSync &hs) {
-    HaloTurn t;
-    t.want = 0;
-    t.prev = 0;
-    if (hs.nnbr == 0 && hs.nsend == 0) return t;
-    if (hs.nnbr > 0) t.want = *reinterpret_cast<const volatile sparsh_u64 *>(hs.expect) + 1;
-    if (hs.nsend > 0) t.prev = *reinterpret_cast<const volatile sparsh_u64 *>(hs.seq);
-    const int tid = threadIdx.x;
-    if (tid < hs.nnbr) spin_ge(hs.flag_local[tid], t.want, hs.err);                          // slices have landed
-    // The fused push writes into the ping-pong partner of the vector being read, whose halo segment last held slice
-    // prev-1 (slice prev is the one this very kernel consumes): everything up to prev-1 must have been consumed.
-    // Waiting for slice prev itself would deadlock — both neighbours only ack it when this sweep ends.
-    if (tid >= 8 && tid - 8 < hs.nsend) spin_ge(hs.ack_local[tid - 8], t.prev > 0 ? t.prev - 1 : 0, hs.err);
-    __syncthreads();
-    return t;
-}
-// called by every thread of the CTA after its last read of x and its last remote store
-__device__ __forceinline__ void halo_done(const HaloSync &hs, const HaloTurn &t) {
-    if (hs.nnbr == 0 && hs.nsend == 0) return;
-    if (hs.nsend > 0) __threadfence_system();  // my remote stores are performed before anyone sees the flag
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int k = atomicAdd(hs.ticket, 1u);
-        if (k == gridDim.x - 1) {
-            if (hs.nnbr > 0) {
-                *reinterpret_cast<volatile sparsh_u64 *>(hs.expect) = t.want;
-                for (int q = 0; q < hs.nnbr; q++) st_release_sys_u64(hs.ack_dst[q], t.want);
-            }
-            if (hs.nsend > 0) {
-                __threadfence_system();
-                for (int q = 0; q < hs.nsend; q++) st_release_sys_u64(hs.flag_dst[q], t.prev + 1);
-                *reinterpret_cast<volatile sparsh_u64 *>(hs.seq) = t.prev + 1;
-            }
-            *hs.ticket = 0u;
-            __threadfence();
-        }
-    }
-}
-__device__ __forceinline__ void block_rows(const RowRange &rr, int rows_per_cta, int &first, int &end) {
-    int blk = blockIdx.x;
-    first = rr.b1;
-    end = rr.e1;
-    if (blk >= rr.nblk1) {
-        blk -= rr.nblk1;
-        first = rr.b2;
-        end = rr.e2;
-    }
-    first += blk * rows_per_cta;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Epilogues.  Arithmetic and evaluation order follow the reference's CPU path:
-//   store_residual   r = b - (A x)                              src/AMG_cycle_utilities.cpp:120-121
-//   jacobi           x += (omega*(b - A x))/d                   src/AMG_smoothers.cpp:62-71
-//   transfer_solution xf = (P xc) + xf                          src/AMG_cycle_utilities.cpp:111
-//   sor (one colour) x -= (omega*((A x) - b))/d                 src/AMG_smoothers.cpp:90-98
-//   residual         ||(A x) - b||                              src/AMG_cycle_utilities.cpp:88-92
-// ---------------------------------------------------------------------------------------------------------
-struct EpiRegs {
-    double b, xi, d;
-};
-
-template <int EPI, bool LOAD_D = true>
-__device__ __forceinline__ EpiRegs epi_load(const EpiArgs &a, const double *y, int row) {
-    EpiRegs e;
-    e.b = 0.0;
-    e.xi = 0.0;
-    e.d = 1.0;
-    if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM) e.b = a.b[row];
-    if (EPI == EPI_JACOBI || EPI == EPI_SPMV_DOT) e.xi = a.xi[row];
-    if (EPI == EPI_PROLONG || EPI == EPI_SOR) e.xi = y[row];
-    if (LOAD_D && (EPI == EPI_JACOBI || EPI == EPI_SOR)) e.d = a.d[row];
-    return e;
-}
-
-// returns this row's contribution to the fused reduction (0 when the epilogue has none)
-template <int EPI, bool PUSH>
-__device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, double s, double *y, int row) {
-    if (EPI == EPI_SPMV) {
-        y[row] = s;
-    } else if (EPI == EPI_RESID) {
-        y[row] = __dsub_rn(e.b, s);
-    } else if (EPI == EPI_JACOBI) {
-        double h = __dsub_rn(e.b, s);
-        const double v = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
-        y[row] = v;
-        if (PUSH && a.pm_ptr) {  // fused halo push: the neighbours' next sweep reads this entry
-            for (int k = a.pm_ptr[row]; k < a.pm_ptr[row + 1]; k++) a.pm_dst[a.pm_nbr[k]][a.pm_off[k]] = v;
-        }
-    } else if (EPI == EPI_PROLONG) {
-        y[row] = __dadd_rn(s, e.xi);
-    } else if (EPI == EPI_SOR) {
-        double h = __dsub_rn(s, e.b);
-        y[row] = __dsub_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
-    } else if (EPI == EPI_SPMV_DOT) {
-        y[row] = s;
-        return __dmul_rn(e.xi, s);
-    } else if (EPI == EPI_RESNORM) {
-        double h = __dsub_rn(s, e.b);
-        return __dmul_rn(h, h);
-    }
-    return 0.0;
-}
-
-template <int EPI>
-struct EpiTraits {
-    static constexpr bool reduces = (EPI == EPI_SPMV_DOT || EPI == EPI_RESNORM);
-    // multicolour SOR updates x in place: its gathers must not use the non-coherent path
-    static constexpr bool coherent_x = (EPI == EPI_SOR);
-};
-
-template <bool COHERENT>
-__device__ __forceinline__ double load_x(const double *x, int c) {
-    if (COHERENT) return x[c];
-    return __ldg(x + c);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Deterministic two-stage reduction: fixed shuffle tree per block, block partials to global memory, then one CTA
-// adds the partials in index order.  The result does not depend on block scheduling: bit-reproducible run to run.
-// ---------------------------------------------------------------------------------------------------------
-template <int THREADS>
-__device__ __forceinline__ double block_sum(double v, double *sred) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();  // sred may still be read from a previous call
-    if (lane == 0) sred[warp] = v;
-    __syncthreads();
-    v = (threadIdx.x < THREADS / 32) ? sred[threadIdx.x] : 0.0;
-    if (warp == 0) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    }
-    return v;  // valid in thread 0
-}
-
-// stage 1: one partial per block (fixed shuffle tree)
-template <int THREADS>
-__device__ __forceinline__ void block_partial(double contrib, double *partials) {
-    __shared__ double sred[32];
-    double v = block_sum<THREADS>(contrib, sred);
-    if (threadIdx.x == 0) partials[blockIdx.x] = v;
-}
 
 // stage 2: a single CTA adds the partials in index order (65536 per-block atomics on one ticket cost ~60 us on a
 // 256^3 SpMV; this kernel costs ~4 us and keeps the result independent of block scheduling)
@@ -288,6 +78,7 @@ __global__ void __launch_bounds__(THREADS)
     }
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);  // multi-GPU: neighbours' halo slices have landed
+    const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     __syncthreads();  // barrier init and s_a0 visible to everyone
     mbar_wait(&bar, 0);
 
@@ -302,13 +93,13 @@ __global__ void __launch_bounds__(THREADS)
                 const bool ok = k + j < hi - a0;
                 v[j] = ok ? sval[k + j] : 0.0;
                 const int c = ok ? scol[k + j] : 0;
-                xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+                xv[j] = ok ? load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, c, hs.halo_begin) : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < 8; j++)
                 if (k + j < hi - a0) s = __dadd_rn(s, __dmul_rn(v[j], xv[j]));
         }
-        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -371,6 +162,7 @@ __global__ void __launch_bounds__(THREADS)
     }
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);
+    const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     __syncthreads();  // barrier init, s_a0 and the dictionaries visible to everyone
     mbar_wait(&bar, 0);
 
@@ -389,14 +181,14 @@ __global__ void __launch_bounds__(THREADS)
                     const unsigned int code = ok ? scode[k + j] : 0u;
                     v[j] = ok ? sdv[code >> 8] : 0.0;
                     const int c = ok ? row + sdo[code & 255u] : 0;
-                    xv[j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+                    xv[j] = ok ? load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, c, hs.halo_begin) : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     if (k + j < hi[s] - a0) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
             }
             // reduction contributions are added in row order within the thread: still a fixed tree
-            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row));
+            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row, strip_cta));
         }
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
@@ -453,6 +245,7 @@ __global__ void __launch_bounds__(THREADS)
     for (int i = tid; i <= P.n_pat; i += THREADS) sstart[i] = __ldg(P.start + i);
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);
+    const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     __syncthreads();  // the table is in place
 
     // The RPT rows of a thread advance together, JB entries each per step: RPT*JB independent gathers are in flight
@@ -481,7 +274,7 @@ __global__ void __launch_bounds__(THREADS)
                 const bool ok = k + j < len[s];
                 v[s][j] = ok ? sval[st[s] + k + j] : 0.0;
                 const int c = ok ? r0 + s * THREADS + tid + soff[st[s] + k + j] : 0;
-                xv[s][j] = ok ? load_x<EpiTraits<EPI>::coherent_x>(x, c) : 0.0;
+                xv[s][j] = ok ? load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, c, hs.halo_begin) : 0.0;
             }
 #pragma unroll
         for (int s = 0; s < RPT; s++)
@@ -500,11 +293,11 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll 1  // rare path: keep it out of the instruction cache's way
                 for (int k = lo; k < hi; k++)
                     sum[s] = __dadd_rn(sum[s], __dmul_rn(__ldg(A.val + k),
-                                                         load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
+                                                         load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
                 if (NEEDS_D) e[s].d = args.d[row];
             }
             // reduction contributions are added in row order within the thread: still a fixed tree
-            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum[s], y, row));
+            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum[s], y, row, strip_cta));
         }
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
@@ -635,14 +428,15 @@ __global__ void __launch_bounds__(THREADS)
     const int row = r0 + threadIdx.x;
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);
+    const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     double contrib = 0.0;
     if (row < row_end) {
         const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
         EpiRegs e = epi_load<EPI>(args, y, row);
         double s = 0.0;
         for (int k = lo; k < hi; k++)
-            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
-        contrib = epi_store<EPI, DIST>(args, e, s, y, row);
+            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -662,18 +456,19 @@ __global__ void __launch_bounds__(256)
     const bool active = row < row_end;
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);
+    const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     double s = 0.0;
     EpiRegs e;
     if (active) {
         const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
         if (lane == 0) e = epi_load<EPI>(args, y, row);
         for (int k = lo + lane; k < hi; k += LANES)
-            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_x<EpiTraits<EPI>::coherent_x>(x, __ldg(A.col + k))));
+            s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
     }
 #pragma unroll
     for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LANES);
     double contrib = 0.0;
-    if (active && lane == 0) contrib = epi_store<EPI, DIST>(args, e, s, y, row);
+    if (active && lane == 0) contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
     if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
 }
@@ -681,29 +476,19 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
-struct LaunchDesc {
-    RowRange rr;
-    int rows1, rows2;
-    HaloSync hs;
-    bool dist = false;  // multi-GPU variant of the kernel (handshake + fused push compiled in)
-};
-
-static int grid_for(LaunchDesc &d, int rows_per_cta) {
-    const int n1 = (d.rows1 + rows_per_cta - 1) / rows_per_cta, n2 = (d.rows2 + rows_per_cta - 1) / rows_per_cta;
-    d.rr.nblk1 = n1;
-    return n1 + n2;
+int launch_finalize_partials(int count, double *out) {
+    Context &c = ctx();
+    finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, count, out);
+    count_launch();
+    SP_CUDA(cudaGetLastError());
+    return SPARSH_OK;
 }
 
 template <int EPI>
 static int finish_launch(int grid, const EpiArgs &args) {
-    Context &c = ctx();
     count_launch();
     SP_CUDA(cudaGetLastError());
-    if (EpiTraits<EPI>::reduces) {
-        finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, grid, args.red_out);
-        count_launch();
-        SP_CUDA(cudaGetLastError());
-    }
+    if (EpiTraits<EPI>::reduces) return launch_finalize_partials(grid, args.red_out);
     return SPARSH_OK;
 }
 
@@ -857,6 +642,8 @@ static int launch_pattern(const sparsh_matrix_s *A, const double *x, double *y, 
     if (pattern_tma() && !d.dist && A->pat_windows.nwin > 0 && (A->nrow & 1) == 0 && (A->ncol & 1) == 0 &&
         ((uintptr_t)x & 15) == 0 && (!needs_b || ((uintptr_t)args.b & 15) == 0))
         return launch_pattern_tma<EPI>(A, x, y, args, d);
+    // lean variant (spmv_pattern.cu): one dominant pattern, gathers issued before the pattern byte is known
+    if (!pattern_tma() && pattern_lean_applies(A)) return launch_pattern_lean(A, EPI, x, y, args, d);
     const int rpt = pattern_rpt();
     if (pattern_jb() == 4) {
         if (rpt == 2) return launch_pattern_cfg<THREADS, 2, 4, EPI>(A, x, y, args, d);
@@ -904,7 +691,7 @@ static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, c
 
 template <int EPI>
 static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
-    if (d.rows1 + d.rows2 <= 0) {
+    if (d.rows1 + d.rows2 + d.rows3 <= 0) {
         if (EpiTraits<EPI>::reduces) SP_CUDA(cudaMemsetAsync(args.red_out, 0, sizeof(double), ctx().stream));
         return SPARSH_OK;
     }
@@ -933,12 +720,13 @@ static int launch_epi(const sparsh_matrix_s *A, const double *x, double *y, cons
     }
 }
 
-int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
-                int b2, int e2, const HaloSync *hs) {
+int launch_csr3(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int b1, int e1,
+                int b2, int e2, int b3, int e3, const HaloSync *hs) {
     LaunchDesc d;
-    d.rr = RowRange{b1, e1, b2, e2, 0};
+    d.rr = RowRange{b1, e1, b2, e2, b3, e3, 0, 0};
     d.rows1 = e1 > b1 ? e1 - b1 : 0;
     d.rows2 = e2 > b2 ? e2 - b2 : 0;
+    d.rows3 = e3 > b3 ? e3 - b3 : 0;
     if (hs) d.hs = *hs;
     d.dist = d.hs.nnbr > 0 || d.hs.nsend > 0;
     if (d.hs.nnbr > 0 && d.rows1 + d.rows2 <= 0) {
@@ -967,7 +755,7 @@ int launch_csr2(const sparsh_matrix_s *A, int epi, const double *x, double *y, c
 
 int launch_csr(const sparsh_matrix_s *A, int epi, const double *x, double *y, const EpiArgs &args, int row_begin,
                int row_end) {
-    return launch_csr2(A, epi, x, y, args, row_begin, row_end, 0, 0, nullptr);
+    return launch_csr3(A, epi, x, y, args, row_begin, row_end, 0, 0, 0, 0, nullptr);
 }
 
 }  // namespace sparsh
