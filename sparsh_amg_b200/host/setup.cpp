@@ -16,6 +16,7 @@
 #include <iostream>
 #include <memory>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 
 #include "sparsh_amg.hpp"
@@ -618,24 +619,37 @@ void reorder_rhs(sp_matrix_mg &A, double *&b) {
 // ---------------------------------------------------------------------------------------------------------
 // AMG_solver: hierarchy construction
 // ---------------------------------------------------------------------------------------------------------
-AMG_solver::AMG_solver() {
-    const int cap = std::max(options().max_levels, 1);
-    Av = new sp_matrix_mg *[cap]();
-    Pv = new sp_matrix_mg *[cap]();
-    Xv = new double *[cap]();
-    Bv = new double *[cap]();
-    Rv = new double *[cap]();
+AMG_solver::AMG_solver() { reserve_levels(std::max(options().max_levels, 1)); }
+
+// The per-level arrays belong to the object, not to the option that happened to be set when it was constructed:
+// options().max_levels may be raised between construction and setup (the reference's level1 is a compile-time macro).
+void AMG_solver::reserve_levels(int nlevels) {
+    if (nlevels <= capacity) return;
+    auto grow = [&](auto *&arr) {
+        using T = std::remove_reference_t<decltype(arr[0])>;
+        T *bigger = new T[nlevels]();
+        for (int k = 0; k < capacity; k++) bigger[k] = arr[k];
+        delete[] arr;
+        arr = bigger;
+    };
+    grow(Av);
+    grow(Pv);
+    grow(Xv);
+    grow(Bv);
+    grow(Rv);
+    capacity = nlevels;
 }
 
 static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
     const sparsh::Options &o = options();
     const double t0 = omp_get_wtime();
     S.l = 0;
+    S.reserve_levels(std::max(o.max_levels, 1));
     S.Av[0] = &A;  // borrowed, as in the reference (src/AMG_phases.cpp:40)
     if (o.print_setup) std::cout << "AMG Setup Phase Details " << (colour ? "SOR Smoother" : "Jacobi smoother") << std::endl;
     if (colour) S.Av[0]->color_matrix_and_reorder();
     int l = 0;
-    while (S.Av[l]->nrow > o.coarse_upper && l < o.max_levels - 1) {
+    while (S.Av[l]->nrow > o.coarse_upper && l < o.max_levels - 1 && l < S.capacity - 1) {
         if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
         if (o.coarsening == sparsh::COARSEN_BECK)
             sequential::beck_prolongator(*S.Av[l], S.Pv[l]);

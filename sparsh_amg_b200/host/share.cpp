@@ -135,8 +135,8 @@ void *sparsh_host_amg_load(const char *dir_c) {
     std::ifstream meta(dir + "/meta.txt");
     int nlev = 0;
     if (!(meta >> nlev) || nlev < 1) return nullptr;
-    if (sparsh::options().max_levels < nlev) sparsh::options().max_levels = nlev;
     AMG_GPU1_solver *S = new AMG_GPU1_solver();
+    S->reserve_levels(nlev);  // sized from the file, the global option is left alone
     SharedState *st = new SharedState();
     S->shared_mapping = st;
     S->l = nlev - 1;

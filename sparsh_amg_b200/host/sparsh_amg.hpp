@@ -184,8 +184,10 @@ class AMG_solver {
     sparsh_hierarchy_s *device = nullptr;  // resident device hierarchy (created on first solve / GPU_Allocations)
     bool torn_down = false;
     void *shared_mapping = nullptr;  // set when the hierarchy's arrays live in files mapped read-only (host/share.cpp)
+    int capacity = 0;                // slots of Av/Pv/Xv/Bv/Rv (the reference sizes them with the macro level1)
 
     AMG_solver();
+    void reserve_levels(int nlevels);  // grow the per-level arrays (contents kept); setup and load call it
     void AMG_solver_setup_jacobi(sp_matrix_mg &A);
     void AMG_solver_setup_SOR(sp_matrix_mg &A);
     // host b, x (x in/out).  iterations > 0: exactly that many V-cycles; -1: until ||r|| <= tolerance.

@@ -191,7 +191,15 @@ def test_shared_hierarchy_roundtrip_and_plans(host, oracle, tmp_path):
     amg = host.HostAmg(A)
     d = str(tmp_path / "hier")
     amg.save(d)
+    # the loaded object sizes its per-level arrays from the file, whatever max_levels says at that moment (a solver
+    # constructed under a smaller max_levels used to overrun them), and leaves the global option alone
+    assert amg.nlevels > 2
+    host.set_options(max_levels=2)
     shared = host.HostAmg.load(d)
+    two = host.HostAmg(A)
+    assert two.nlevels == 2  # max_levels = 2 still governs a fresh setup
+    two.free()
+    host.set_options(max_levels=32)
     assert shared.nlevels == amg.nlevels
     for L0, L1 in zip(amg.levels(), shared.levels()):
         for key in ("rowptr", "colindex", "val"):
