@@ -485,6 +485,30 @@ int nccl_finish() {
     return SPARSH_OK;
 }
 
+// two-launch variant (SPARSH_DIST_MERGE=0, kept for A/B measurements): strips on the auxiliary stream, interior rows on
+// the main stream, joined by events
+struct StreamSwap {
+    cudaStream_t saved;
+    explicit StreamSwap(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
+    ~StreamSwap() { ctx().stream = saved; }
+};
+int fork_aux() {
+    Comm &m = comm();
+    SP_CUDA(cudaEventRecord(m.ev_ready, ctx().stream));
+    SP_CUDA(cudaStreamWaitEvent(m.comm_stream, m.ev_ready, 0));
+    return SPARSH_OK;
+}
+int join_aux() {
+    Comm &m = comm();
+    SP_CUDA(cudaEventRecord(m.ev_done, m.comm_stream));
+    SP_CUDA(cudaStreamWaitEvent(ctx().stream, m.ev_done, 0));
+    return SPARSH_OK;
+}
+bool env_on(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) != 0 : dflt;
+}
+
 // y = epi(op x).  The rows that touch the halo (and, for the fused Jacobi, the rows a neighbour needs) form the two
 // boundary strips, everything else is interior.  Peer mode: a generic push first if the halo of x is not already on
 // its way, then ONE launch — the strip CTAs come first in the grid, wait for the flags, compute, optionally store the
@@ -532,6 +556,19 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
         hs.seq = h->seq + op.id;
         h->halo_ready[by] = op.id + 1;
     }
+    static const bool merge = env_on("SPARSH_DIST_MERGE", true);
+    if (!merge && split && !reduces) {
+        EpiArgs iargs = args;  // interior rows: nothing to send
+        iargs.pm_ptr = nullptr;
+        SP_TRY(fork_aux());
+        {
+            StreamSwap sw(m.comm_stream);
+            if (need_push) SP_TRY(peer_push(h, op, x));
+            SP_TRY(launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, 0, 0, &hs));
+        }
+        SP_TRY(launch_csr(op.M, epi, x, y, iargs, op.ib, op.ie));
+        return join_aux();
+    }
     if (need_push) SP_TRY(peer_push(h, op, x));
     if (!split) return launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
     return launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
@@ -551,7 +588,8 @@ PeerTab peer_tab(const sparsh_dist_s *h) {
 int allreduce_sum(sparsh_dist_s *h, double *d_vals, int count) {
     Comm &m = comm();
     if (m.nranks == 1) return SPARSH_OK;
-    if (h->peer) {
+    static const bool peer_coll = env_on("SPARSH_PEER_COLL", true);
+    if (h->peer && peer_coll) {
         SP_REQUIRE(count >= 1 && count < RED_SLOTS, "peer all-reduce handles up to 3 scalars");
         peer_allreduce_kernel<<<1, 32, 0, ctx().stream>>>(d_vals, count, peer_tab(h), h->coll_off, h->red_seq, h->d_err, h->timeout_ns);
         count_launch();
@@ -611,7 +649,8 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
     // replicated tail: every rank contributes its part of the restricted right-hand side to all copies of the vector,
     // the levels below are solved redundantly, the owned rows of the correction are kept
     const int gblocks = std::max(1, std::min((h->n_own_tail0 + 255) / 256, 4 * c.sm_count));
-    if (m.nranks > 1 && h->peer) {
+    static const bool peer_coll = env_on("SPARSH_PEER_COLL", true);
+    if (m.nranks > 1 && h->peer && peer_coll) {
         tail_exchange_kernel<<<gblocks, 256, 0, c.stream>>>(h->btail_local, h->d_tail_rows, h->n_own_tail0, peer_tab(h), h->tailb_off,
                                                             h->coll_off, h->tail_seq, h->tail_ticket, h->d_err, h->timeout_ns);
         count_launch();
@@ -627,7 +666,7 @@ int enqueue_dist_vcycle(sparsh_dist_s *h, const double *b, double *x, bool x_is_
         count_launch();
     }
     SP_TRY(enqueue_vcycle(h->tail, h->tail_b, h->tail_x, true));
-    if (m.nranks > 1 && h->peer) {
+    if (m.nranks > 1 && h->peer && peer_coll) {
         tail_gather_ack_kernel<<<gblocks, 256, 0, c.stream>>>(h->tail_x, h->d_tail_rows, h->n_own_tail0, h->xtail_local, peer_tab(h),
                                                               h->coll_off, h->tail_seq);
         count_launch();

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(THREADS)
         }
         contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
     }
+    if (pushes<EPI, DIST>(args, strip_cta) && active) fused_push<EPI, DIST>(args, y, row);
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
 }
@@ -190,6 +191,11 @@ __global__ void __launch_bounds__(THREADS)
             // reduction contributions are added in row order within the thread: still a fixed tree
             contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row, strip_cta));
         }
+    }
+    if (pushes<EPI, DIST>(args, strip_cta)) {
+#pragma unroll 1
+        for (int s = 0; s < RPT; s++)
+            if (s * THREADS + tid < nrows) fused_push<EPI, DIST>(args, y, r0 + s * THREADS + tid);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -299,6 +305,11 @@ __global__ void __launch_bounds__(THREADS)
             // reduction contributions are added in row order within the thread: still a fixed tree
             contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum[s], y, row, strip_cta));
         }
+    }
+    if (pushes<EPI, DIST>(args, strip_cta)) {
+#pragma unroll 1
+        for (int s = 0; s < RPT; s++)
+            if (pid[s] >= 0) fused_push<EPI, DIST>(args, y, r0 + s * THREADS + tid);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -437,6 +448,7 @@ __global__ void __launch_bounds__(THREADS)
         for (int k = lo; k < hi; k++)
             s = __dadd_rn(s, __dmul_rn(__ldg(A.val + k), load_xd<EpiTraits<EPI>::coherent_x, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
         contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
+        if (pushes<EPI, DIST>(args, strip_cta)) fused_push<EPI, DIST>(args, y, row);
     }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
@@ -468,7 +480,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LANES);
     double contrib = 0.0;
-    if (active && lane == 0) contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
+    if (active && lane == 0) {
+        contrib = epi_store<EPI, DIST>(args, e, s, y, row, strip_cta);
+        if (pushes<EPI, DIST>(args, strip_cta)) fused_push<EPI, DIST>(args, y, row);
+    }
     if (EpiTraits<EPI>::reduces) block_partial<256>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
 }

@@ -168,10 +168,7 @@ __device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, 
     } else if (EPI == EPI_JACOBI) {
         double h = __dsub_rn(e.b, s);
         const double v = __dadd_rn(e.xi, __ddiv_rn(__dmul_rn(a.omega, h), e.d));
-        y[row] = v;
-        if (PUSH && strip && a.pm_ptr) {  // fused halo push: the neighbours' next sweep reads this entry
-            for (int k = a.pm_ptr[row]; k < a.pm_ptr[row + 1]; k++) a.pm_dst[a.pm_nbr[k]][a.pm_off[k]] = v;
-        }
+        y[row] = v;  // (multi-GPU: the boundary strips push it to the neighbours afterwards, see fused_push)
     } else if (EPI == EPI_PROLONG) {
         y[row] = __dadd_rn(s, e.xi);
     } else if (EPI == EPI_SOR) {
@@ -187,6 +184,25 @@ __device__ __forceinline__ double epi_store(const EpiArgs &a, const EpiRegs &e, 
     return 0.0;
 }
 
+// Multi-GPU, fused Jacobi + halo exchange: a row whose new value a neighbour needs stores it ALSO into that neighbour's
+// halo segment of the next sweep's input vector (peer store over NVLink).  Called by the strip CTAs for each of their
+// rows AFTER the row sums, as a phase of its own: kept out of the row loop it costs the hot path no register (inside
+// epi_store it took the plain-CSR kernel from 32 to 64 registers, i.e. from 8 to 4 resident CTAs per SM).
+template <int EPI, bool DIST>
+__device__ __forceinline__ void fused_push(const EpiArgs &a, const double *y, int row) {
+    if (DIST && EPI == EPI_JACOBI) {
+        const int lo = a.pm_ptr[row], hi = a.pm_ptr[row + 1];
+        if (lo < hi) {
+            const double v = y[row];  // written by this very thread
+            for (int k = lo; k < hi; k++) a.pm_dst[a.pm_nbr[k]][a.pm_off[k]] = v;
+        }
+    }
+}
+template <int EPI, bool DIST>
+__device__ __forceinline__ bool pushes(const EpiArgs &a, bool strip_cta) {
+    return DIST && EPI == EPI_JACOBI && strip_cta && a.pm_ptr != nullptr;
+}
+
 template <int EPI>
 struct EpiTraits {
     static constexpr bool reduces = (EPI == EPI_SPMV_DOT || EPI == EPI_RESNORM);
@@ -199,12 +215,14 @@ __device__ __forceinline__ double load_x(const double *x, int c) {
     if (COHERENT) return x[c];
     return __ldg(x + c);
 }
-// multi-GPU kernels: halo entries (c >= halo_begin) are written by peers while the grid may already be resident, so the
-// non-coherent path (and a stale L1 sector the interior rows of a co-resident CTA pulled in) is off limits for them
+// multi-GPU kernels: halo entries are written by peers over NVLink while the grid may already be resident, so the
+// non-coherent path (ld.global.nc: data must be read-only for the kernel's lifetime) is off limits for the gathered
+// vector.  Plain loads are ordered behind the flag acquire + CTA barrier of halo_wait, and a stale L1 line cannot exist:
+// halo segments start on 128-byte boundaries (dist.cu), no CTA reads a halo entry before its flags are up, and interior
+// CTAs never reference one.  (halo_begin is kept for kernels that want to tell the two apart.)
 template <bool COHERENT, bool DIST>
-__device__ __forceinline__ double load_xd(const double *x, int c, int halo_begin) {
-    if (COHERENT) return x[c];
-    if (DIST && c >= halo_begin) return __ldcg(x + c);
+__device__ __forceinline__ double load_xd(const double *x, int c, int /*halo_begin*/) {
+    if (COHERENT || DIST) return x[c];
     return __ldg(x + c);
 }
 

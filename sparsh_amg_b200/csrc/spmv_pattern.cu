@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(THREADS)
             }
         }
     }
+    if (pushes<EPI, DIST>(args, strip_cta)) {
+#pragma unroll 1
+        for (int s = 0; s < RPT; s++)
+            if (pid[s] >= 0) fused_push<EPI, DIST>(args, y, r0 + s * THREADS + tid);
+    }
     if (EpiTraits<EPI>::reduces) block_partial<THREADS>(contrib, partials);
     if (DIST) halo_done(hs, hs_turn);
 }
