@@ -72,11 +72,15 @@ int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *h_row
 int sparsh_matrix_destroy(sparsh_matrix_t A); /* sp_matrix_gpu::~sp_matrix_gpu (src/AMG_gpu_matrix.cu:131-142) */
 int sparsh_matrix_dims(sparsh_matrix_t A, int *nrow, int *ncol, int *nnz);
 /* kernel family chosen at upload: 0 scalar (<=2.5 nnz/row), 1 stream (TMA-staged, thread per row), 2 vector
- * (sub-warp per row), 3 dict (stream kernel over the csr-dict16 twin below, chosen whenever the twin exists),
- * 4 pattern (csr-pattern8 twin below; built only when the environment sets SPARSH_PATTERN=1|2, selected with 1).
+ * (sub-warp per row), 3 dict (stream kernel over the csr-dict16 twin below, when that twin exists), 4 pattern
+ * (csr-pattern8 twin below, preferred over dict when the rows repeat; SPARSH_PATTERN=0 disables it, =2 builds the twin
+ * without selecting it).
  * sparsh_matrix_force_kernel overrides it (tests exercise every family). */
 int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, int *smem_bytes);
 int sparsh_matrix_force_kernel(sparsh_matrix_t A, int kind, int threads_or_lanes);
+/* name of the kernel instantiation the library launches for this matrix and epilogue (0 SpMV, 1 residual, 2 Jacobi,
+ * 3 prolongation-correction, 4 SOR colour, 5 SpMV+dot, 6 residual norm): for reports */
+int sparsh_matrix_kernel_name(sparsh_matrix_t A, int epilogue, char *buf, size_t len);
 
 /* csr-dict16, the lossless storage the stream kernel prefers: entry j of row i is stored as the 16-bit code
  * (vi << 8) | oi with val[j] == dict_val[vi] (compared by bit pattern) and colindex[j] == i + dict_off[oi]; rowptr is
@@ -280,6 +284,16 @@ int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_loc
 /* distributed AMG-PCG: same arithmetic as sparsh_hierarchy_pcg, dots completed by ncclAllReduce */
 int sparsh_dist_pcg(sparsh_dist_t h, const double *d_b_local, double *d_x_local, double tol, int max_iter,
                     double *h_hist, int *iters);
+/* distributed twins of sparsh_hierarchy_amg_solve (AMG as a solver, AMG_solve_jacobi(b,x,-1), src/AMG_phases.cpp:194-226)
+ * and of sparsh_hierarchy_pbicgstab (Solver_PBiCG_1, src/AMG_main_solvers.cpp:358-458): same arithmetic on the local
+ * row blocks, residual norms and dot products completed across the ranks */
+/* assemble a row-distributed HOST vector on every rank: h_full[h_rows[i]] = h_local[i] over the rows of all ranks (result
+ * collection for reference-style callers that hold global b and x; setup-time collective, not on the solve path) */
+int sparsh_dist_allgather_rows(const double *h_local, const int *h_rows, int n_local, double *h_full, int n_full);
+int sparsh_dist_amg_solve(sparsh_dist_t h, const double *d_b_local, double *d_x_local, double tol, int max_cycles,
+                          double *h_hist, int *cycles);
+int sparsh_dist_pbicgstab(sparsh_dist_t h, const double *d_b_local, double *d_x_local, double tol, int max_iter,
+                          double *h_hist, int *iters);
 
 #ifdef __cplusplus
 }

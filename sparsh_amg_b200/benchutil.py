@@ -37,9 +37,9 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def kernel_label(M, epi):
-    kind, tl, _ = M.kernel()
-    return f"{KIND_NAME[kind]}<{tl},{epi}>"
+def kernel_label(M, op):
+    """the kernel instantiation the library launches for `op` on M (asked from the library itself)"""
+    return M.kernel_name({"restrict": "spmv"}.get(op, op))
 
 
 def csr_bytes(op, nrow, ncol, nnz):
@@ -101,7 +101,7 @@ def roofline_jacobi(torch, stream, lib, A0, db, dx, dt, grid, reps=20, where="le
     peak, peak_kind = measured_peak()
     stored, alg = stored_bytes(kind, "jacobi", n, m, z), csr_bytes("jacobi", n, m, z)
     traffic = jacobi_traffic(grid, kind) if where == "level 0" else None
-    out = {"bound": "hbm", "kernel": f"{KIND_NAME[kind]}<{tl},EPI_JACOBI> (fused Jacobi sweep, {where})",
+    out = {"bound": "hbm", "kernel": f"{A0.kernel_name('jacobi')} (fused Jacobi sweep, {where})",
            "achieved": stored / sec / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
            "frac": stored / sec / 1e9 / peak, "traffic": traffic, "bytes_per_launch": stored,
            "ms_per_launch": sec * 1e3, "frac_of_8TBs_nominal": stored / sec / 1e9 / 8000.0,
@@ -136,7 +136,7 @@ def kernel_table(torch, stream, lib, dH, db, dx, grid, reps=20):
     def mat_op(op, M, epi, fn, per_call=1):
         kind = M.kernel()[0]
         sec = timed(torch, stream, fn, reps) / per_call
-        add(op, kernel_label(M, epi), sec, stored_bytes(kind, op, M.nrow, M.ncol, M.nnz), csr_bytes(op, M.nrow, M.ncol, M.nnz))
+        add(op, kernel_label(M, op), sec, stored_bytes(kind, op, M.nrow, M.ncol, M.nnz), csr_bytes(op, M.nrow, M.ncol, M.nnz))
 
     mat_op("spmv", A0, "EPI_SPMV", lambda: ck(lib.sparsh_spmv(A0.h, dx.ptr, y.ptr)))
     mat_op("spmv_dot", A0, "EPI_SPMV_DOT", lambda: ck(lib.sparsh_spmv_dot(A0.h, dx.ptr, y.ptr, dsc.ptr)))

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsparsh_b200.so")
+LIB_PATH = os.environ.get("SPARSH_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libsparsh_b200.so")  # (override: kernel experiments)
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -60,6 +60,7 @@ SIGNATURES = {
     "sparsh_matrix_dims": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_kernel": (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     "sparsh_matrix_force_kernel": (_i, [_vp, _i, _i]),
+    "sparsh_matrix_kernel_name": (_i, [_vp, _i, C.c_char_p, _sz]),
     "sparsh_pattern_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p,
                                    c_int_p]),
     "sparsh_pattern_windows": (_i, [_i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, _vp]),
@@ -106,6 +107,9 @@ SIGNATURES = {
     "sparsh_dist_spmv": (_i, [_vp, _i, _vp, _vp]),
     "sparsh_dist_vcycle": (_i, [_vp, _vp, _vp, _i, _i]),
     "sparsh_dist_pcg": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
+    "sparsh_dist_allgather_rows": (_i, [c_dbl_p, c_int_p, _i, c_dbl_p, _i]),
+    "sparsh_dist_amg_solve": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
+    "sparsh_dist_pbicgstab": (_i, [_vp, _vp, _vp, _d, _i, c_dbl_p, c_int_p]),
 }
 
 

@@ -304,6 +304,7 @@ struct sparsh_dist_s {
     double *btail_local = nullptr;
     // Krylov
     double *kv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *bv[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // BiCGStab: vectors no operator gathers from
     double *d_sc = nullptr, *h_sc = nullptr;
     std::vector<GraphEntry> graphs;
     // arena shared through CUDA IPC: [flags | vectors]
@@ -485,8 +486,8 @@ int nccl_finish() {
     return SPARSH_OK;
 }
 
-// two-launch variant (SPARSH_DIST_MERGE=0, kept for A/B measurements): strips on the auxiliary stream, interior rows on
-// the main stream, joined by events
+// the auxiliary stream carries the generic halo pushes (and, with SPARSH_DIST_MERGE=0 — kept for A/B measurements — the
+// boundary strips as a launch of their own beside the interior rows); joined by events
 struct StreamSwap {
     cudaStream_t saved;
     explicit StreamSwap(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
@@ -569,9 +570,22 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
         SP_TRY(launch_csr(op.M, epi, x, y, iargs, op.ib, op.ie));
         return join_aux();
     }
-    if (need_push) SP_TRY(peer_push(h, op, x));
-    if (!split) return launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
-    return launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
+    // A generic push (first sweep after a transfer, residual -> R, x -> P, p -> A p) runs on the auxiliary stream BESIDE
+    // the consuming grid, not in front of it: it waits for the neighbours' acks and feeds THEIR strips; this rank's grid
+    // does not depend on it (its own strips wait for the neighbours' flags), so only the join does.
+    if (need_push) {
+        SP_TRY(fork_aux());
+        StreamSwap sw(m.comm_stream);
+        SP_TRY(peer_push(h, op, x));
+    }
+    int rc;
+    if (!split)
+        rc = launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
+    else
+        rc = launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
+    SP_TRY(rc);
+    if (need_push) SP_TRY(join_aux());
+    return SPARSH_OK;
 }
 
 PeerTab peer_tab(const sparsh_dist_s *h) {
@@ -1096,6 +1110,7 @@ int sparsh_dist_hierarchy_destroy(sparsh_dist_t h) {
     cudaFree(h->ticket);
     cudaFree(h->ticket2);
     cudaFree(h->d_pm_tab);
+    for (int i = 0; i < 7; i++) cudaFree(h->bv[i]);
     cudaFree(h->red_seq);
     cudaFree(h->tail_seq);
     cudaFree(h->tail_ticket);
@@ -1206,6 +1221,167 @@ int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int
     if (iters_out) *iters_out = count;
     if (rc != SPARSH_OK) return rc;
     return r1 <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
+}
+
+// Assemble a row-distributed host vector on every rank: full[rows[i]] = local[i] for the rows of all ranks (setup /
+// result collection for the reference-style entry points whose callers hold global b and x; not on the solve path).
+int sparsh_dist_allgather_rows(const double *h_local, const int *h_rows, int n_local, double *h_full, int n_full) {
+    SP_TRY(ensure_init());
+    Comm &m = comm();
+    SP_REQUIRE(n_local >= 0 && n_full >= 0 && (n_local == 0 || (h_local && h_rows)) && h_full, "bad arguments");
+    if (m.nranks == 1) {
+        for (int i = 0; i < n_local; i++) h_full[h_rows[i]] = h_local[i];
+        return SPARSH_OK;
+    }
+    SP_REQUIRE(m.comm != nullptr, "sparsh_dist_init has not been called");
+    std::vector<char> all;
+    SP_TRY(allgather_bytes(&n_local, sizeof n_local, all));
+    int maxc = 1;
+    std::vector<int> counts((size_t)m.nranks);
+    for (int r = 0; r < m.nranks; r++) {
+        std::memcpy(&counts[r], all.data() + (size_t)r * sizeof(int), sizeof(int));
+        maxc = std::max(maxc, counts[r]);
+    }
+    std::vector<double> vpad((size_t)maxc, 0.0);
+    std::vector<int> rpad((size_t)maxc, -1);
+    std::copy(h_local, h_local + n_local, vpad.begin());
+    std::copy(h_rows, h_rows + n_local, rpad.begin());
+    std::vector<char> vall, rall;
+    SP_TRY(allgather_bytes(vpad.data(), sizeof(double) * (size_t)maxc, vall));
+    SP_TRY(allgather_bytes(rpad.data(), sizeof(int) * (size_t)maxc, rall));
+    for (int r = 0; r < m.nranks; r++) {
+        const double *v = reinterpret_cast<const double *>(vall.data() + (size_t)r * sizeof(double) * (size_t)maxc);
+        const int *ri = reinterpret_cast<const int *>(rall.data() + (size_t)r * sizeof(int) * (size_t)maxc);
+        for (int i = 0; i < counts[r]; i++) {
+            SP_REQUIRE(ri[i] >= 0 && ri[i] < n_full, "row id out of range in the gathered vector");
+            h_full[ri[i]] = v[i];
+        }
+    }
+    return SPARSH_OK;
+}
+
+// AMG as a solver on the row-partitioned hierarchy: V-cycles until ||A x - b||_2 <= tol (absolute, as the reference:
+// AMG_solver::AMG_solve_jacobi(b,x,-1), src/AMG_phases.cpp:194-226; single-GPU twin: sparsh_hierarchy_amg_solve).  One
+// graph launch per cycle: the cycle, the fused residual-norm kernel over the local rows, the all-reduce.
+int sparsh_dist_amg_solve(sparsh_dist_t h, const double *b, double *x, double tol, int max_cycles, double *hist, int *cycles_out) {
+    SP_TRY(check_alive(h));
+    Context &c = ctx();
+    DistLevel &L0 = h->lev[0];
+    const size_t n = (size_t)L0.n;
+    double *xs = h->kv[4];
+    double *sc = h->d_sc;
+    enum { S_RES = 3 };
+    auto resnorm = [&]() -> int {  // ||A x - b||^2 over all ranks -> h_sc[S_RES]  (reference :159, :219)
+        EpiArgs a;
+        a.b = b;
+        a.red_out = sc + S_RES;
+        SP_TRY(apply(h, L0.A, EPI_RESNORM, xs, nullptr, a));
+        SP_TRY(allreduce_sum(h, sc + S_RES, 1));
+        SP_CUDA(cudaMemcpyAsync(h->h_sc + S_RES, sc + S_RES, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (h->peer) SP_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        return SPARSH_OK;
+    };
+    SP_CUDA(cudaMemcpyAsync(xs, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    SP_TRY(resnorm());
+    SP_CUDA(cudaStreamSynchronize(c.stream));
+    double r1 = std::sqrt(h->h_sc[S_RES]);
+    if (hist) hist[0] = r1;
+    auto body = [&]() -> int {
+        SP_TRY(enqueue_dist_vcycle(h, b, xs, false));
+        return resnorm();
+    };
+    int cycles = 0, rc = SPARSH_OK;
+    while (r1 > tol && cycles < max_cycles) {  // :196 (the reference has no cap: SURVEY F6)
+        SP_TRY(dist_run_graphed(h, b, xs, 30, body));
+        SP_CUDA(cudaStreamSynchronize(c.stream));
+        cycles++;
+        if (h->peer && *h->h_err) {
+            h->dead = true;
+            set_error("multi-GPU halo handshake timed out (a neighbour never signalled); the distributed handle is unusable");
+            rc = SPARSH_ERR_CUDA;
+            break;
+        }
+        r1 = std::sqrt(h->h_sc[S_RES]);
+        if (hist) hist[cycles] = r1;
+        if (!std::isfinite(r1)) break;
+    }
+    SP_CUDA(cudaMemcpyAsync(x, xs, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    SP_CUDA(cudaStreamSynchronize(c.stream));
+    if (cycles_out) *cycles_out = cycles;
+    if (rc != SPARSH_OK) return rc;
+    return r1 <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
+}
+
+// Distributed AMG-preconditioned BiCGStab: the arithmetic of bicg_impl(precond = true) in krylov.cu, i.e. of the
+// reference's Solver_PBiCG_1 (src/AMG_main_solvers.cpp:358-458); each group of dot products is completed by one
+// in-place all-reduce of adjacent device scalars.
+int sparsh_dist_pbicgstab(sparsh_dist_t h, const double *b, double *x, double tol, int max_iter, double *hist, int *iters_out) {
+    SP_TRY(check_alive(h));
+    Context &c = ctx();
+    DistLevel &L0 = h->lev[0];
+    const size_t n = (size_t)L0.n;
+    for (int i = 0; i < 7; i++)
+        if (!h->bv[i]) SP_CUDA(cudaMalloc(&h->bv[i], sizeof(double) * (n + 2)));
+    // ph, sh are gathered from by A (arena vectors with halo segments); the others are purely local
+    double *ph = h->kv[0], *sh = h->kv[1], *xs = h->kv[4];
+    double *r0 = h->bv[0], *r = h->bv[1], *p = h->bv[2], *Ap = h->bv[3], *s = h->bv[4], *As = h->bv[5], *xl = h->bv[6];
+    double *sc = h->d_sc;
+    enum { S_A1 = 4, S_APR0 = 5, S_ASS = 6, S_ASAS = 7, S_RR0 = 8, S_RRN = 9 };  // as in krylov.cu
+    auto read_res = [&]() -> int {
+        SP_CUDA(cudaMemcpyAsync(h->h_sc + S_RRN, sc + S_RRN, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (h->peer) SP_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        return SPARSH_OK;
+    };
+    SP_CUDA(cudaMemcpyAsync(xs, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    SP_CUDA(cudaMemcpyAsync(xl, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    EpiArgs a;
+    a.b = b;
+    SP_TRY(apply(h, L0.A, EPI_RESID, xs, r0, a));                                                 // :383-384
+    SP_CUDA(cudaMemcpyAsync(r, r0, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));      // :387
+    SP_CUDA(cudaMemcpyAsync(p, r0, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));      // :388
+    SP_TRY(k_dot(n, r0, r0, sc + S_RRN));                                                         // :390
+    SP_TRY(allreduce_sum(h, sc + S_RRN, 1));
+    SP_TRY(read_res());
+    SP_CUDA(cudaStreamSynchronize(c.stream));
+    double res = std::sqrt(h->h_sc[S_RRN]);
+    if (hist) hist[0] = res;
+
+    auto body = [&]() -> int {
+        SP_TRY(enqueue_dist_vcycle(h, p, ph, true));                             // :399-400
+        SP_TRY(k_dot(n, r, r0, sc + S_A1));                                      // :402
+        SP_TRY(apply(h, L0.A, EPI_SPMV, ph, Ap, EpiArgs()));                     // :403
+        SP_TRY(k_dot(n, Ap, r0, sc + S_APR0));                                   // :404
+        SP_TRY(allreduce_sum(h, sc + S_A1, 2));                                  // (S_A1, S_APR0 adjacent)
+        SP_TRY(k_bicg_s(n, r, Ap, s, sc + S_A1, sc + S_APR0));                   // :406-411
+        SP_TRY(enqueue_dist_vcycle(h, s, sh, true));                             // :414-415
+        SP_TRY(apply(h, L0.A, EPI_SPMV, sh, As, EpiArgs()));                     // :416
+        SP_TRY(k_dot2(n, As, s, As, sc + S_ASS));                                // :418-419
+        SP_TRY(allreduce_sum(h, sc + S_ASS, 2));
+        SP_TRY(k_bicg_xr(n, xl, ph, sh, s, As, r, sc + S_A1, sc + S_APR0, sc + S_ASS, sc + S_ASAS, r0, sc + S_RR0));  // :424-425
+        SP_TRY(allreduce_sum(h, sc + S_RR0, 2));                                 // r.r0 (:428) and r.r (:437)
+        SP_TRY(k_bicg_p(n, r, p, Ap, sc + S_A1));                                // :428-434
+        return read_res();
+    };
+    int count = 0, rc = SPARSH_OK;
+    while (res > tol && count < max_iter) {  // :397 (no cap in the reference)
+        SP_TRY(dist_run_graphed(h, x, b, 20, body));
+        SP_CUDA(cudaStreamSynchronize(c.stream));
+        count++;
+        if (h->peer && *h->h_err) {
+            h->dead = true;
+            set_error("multi-GPU halo handshake timed out (a neighbour never signalled); the distributed handle is unusable");
+            rc = SPARSH_ERR_CUDA;
+            break;
+        }
+        res = std::sqrt(h->h_sc[S_RRN]);     // :437
+        if (hist) hist[count] = res;
+        if (!std::isfinite(res)) break;
+    }
+    SP_CUDA(cudaMemcpyAsync(x, xl, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    SP_CUDA(cudaStreamSynchronize(c.stream));
+    if (iters_out) *iters_out = count;
+    if (rc != SPARSH_OK) return rc;
+    return res <= tol ? SPARSH_OK : SPARSH_ERR_NOT_CONVERGED;
 }
 
 }  // extern "C"

@@ -143,6 +143,7 @@ struct sparsh_matrix_s {
     // kernel selection (made at upload from host-side row statistics)
     int kind = sparsh::KIND_VECTOR;
     int threads = 256;  // stream/scalar: rows per CTA == threads per CTA
+    bool threads_forced = false;  // set by sparsh_matrix_force_kernel: the caller's launch shape is honoured as given
     int lanes = 8;      // vector: lanes per row
     int max_row = 0;
     double mean_row = 0.0;

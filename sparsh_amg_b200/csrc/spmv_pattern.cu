@@ -12,6 +12,9 @@
 //    address computation, one LDG, one DMUL and one DADD whose second operands come from the constant bank;
 //  * the table copy into shared memory: done only by CTAs that meet a row with another pattern.
 // Same entries, same order, same unfused arithmetic as the CSR kernels: results are bit-identical.
+#include <algorithm>
+#include <cstdlib>
+
 #include "spmv_common.cuh"
 
 namespace sparsh {
@@ -24,27 +27,65 @@ __device__ __forceinline__ double gather(const double *x, int c, int ncol, int h
     return load_xd<COHERENT, DIST>(x, c, halo_begin);
 }
 
+__device__ __forceinline__ void prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// rows [first, first + count) of virtual block `blk` (the mapping of block_rows for an arbitrary block index)
+__device__ __forceinline__ void virtual_block_rows(const RowRange &rr, int blk, int rows_per_cta, int &first, int &end) {
+    first = rr.b1;
+    end = rr.e1;
+    if (blk >= rr.nblk1) {
+        blk -= rr.nblk1;
+        first = rr.b2;
+        end = rr.e2;
+        if (blk >= rr.nblk2) {
+            blk -= rr.nblk2;
+            first = rr.b3;
+            end = rr.e3;
+        }
+    }
+    first += blk * rows_per_cta;
+}
+
 template <int THREADS, int RPT, int LEN0, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_pat2_kernel(CsrView A, PatView P, const __grid_constant__ Pat0 Z, const double *x, double *y, EpiArgs args,
-                    RowRange rr, double *partials, HaloSync hs) {
+                    RowRange rr, double *partials, HaloSync hs, int pf_dist) {
+    constexpr bool NEEDS_B = (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM);
     constexpr bool NEEDS_D = (EPI == EPI_JACOBI || EPI == EPI_SOR);
     constexpr bool COH = EpiTraits<EPI>::coherent_x;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sval = reinterpret_cast<double *>(smem_raw);   // n_ent values       } only filled by CTAs that own a row
-    double *sdiag = sval + P.n_ent;                        // n_pat              } with another pattern than 0
-    int *soff = reinterpret_cast<int *>(sdiag + P.n_pat);  // n_ent offsets
-    int *sstart = soff + P.n_ent;                          // n_pat + 1
+    constexpr int TILE = THREADS * RPT;
 
     const int tid = threadIdx.x;
     int r0, row_end;
-    block_rows(rr, THREADS * RPT, r0, row_end);
-    const int nrows = min(THREADS * RPT, row_end - r0);
+    block_rows(rr, TILE, r0, row_end);
+    const int nrows = min(TILE, row_end - r0);
+
+    // DRAM latency is paid by somebody else: this CTA asks L2 for the lines of the tile that the CTA taking its place
+    // on the SM will work on (pf_dist = co-resident CTAs of the grid), so that tile's own loads are L2 hits.  What is
+    // new to L2 per tile: its slice of b, of x (offset 0), of the pattern bytes, and the x lines at the largest offset
+    // of pattern 0 (the next grid plane; smaller offsets were gathered by earlier tiles).  One line per thread.
+    if (pf_dist > 0 && (int)blockIdx.x + pf_dist < (int)gridDim.x) {
+        int p0, pend;
+        virtual_block_rows(rr, blockIdx.x + pf_dist, TILE, p0, pend);
+        const int pn = min(TILE, pend - p0);
+        constexpr int LPT = TILE / 16;  // 128-byte lines of doubles per tile
+        if (pn > 0) {
+            const int part = tid / LPT, line = tid % LPT;  // THREADS >= 4 * LPT for RPT <= 4
+            const int i = p0 + line * 16;
+            if (i < p0 + pn) {
+                if (part == 0) prefetch_l2_line(x + i);
+                if (part == 1 && Z.hi > 0 && i + Z.hi < A.ncol) prefetch_l2_line(x + i + Z.hi);
+                if (part == 2 && NEEDS_B) prefetch_l2_line(args.b + i);
+                if (part == 3 && (line & 7) == 0) prefetch_l2_line(P.pat + i);
+            }
+        }
+    }
+
     HaloTurn hs_turn;
     if (DIST) hs_turn = halo_wait(hs);  // multi-GPU: the halo slices have landed before any (speculative) gather
     const bool strip_cta = !DIST || (int)blockIdx.x < hs.nstrip;
     // do the pattern-0 gathers of EVERY row of this tile stay inside the vector?  (CTA-uniform; false only at the ends)
-    const bool safe = r0 + Z.lo >= 0 && r0 + THREADS * RPT - 1 + Z.hi < A.ncol;
+    const bool safe = r0 + Z.lo >= 0 && r0 + TILE - 1 + Z.hi < A.ncol;
     const bool table_d = P.use_pdiag != 0;
 
     int pid[RPT];
@@ -69,52 +110,34 @@ __global__ void __launch_bounds__(THREADS)
     }
 
     double contrib = 0.0;
-    bool other = false;
 #pragma unroll
     for (int s = 0; s < RPT; s++) {
+        if (pid[s] < 0) continue;
+        const int row = r0 + s * THREADS + tid;
+        double sum = 0.0;
         if (pid[s] == 0) {
-            const int row = r0 + s * THREADS + tid;
-            double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < LEN0; k++) sum = __dadd_rn(sum, __dmul_rn(Z.val[k], g[s][k]));
             if (NEEDS_D && table_d) e[s].d = Z.diag;
-            // reduction contributions: pattern-0 rows in row order, then the others in row order — a fixed tree
-            contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row, strip_cta));
-        } else if (pid[s] > 0) {
-            other = true;
-        }
-    }
-
-    if (__syncthreads_or(other)) {  // somebody in this CTA met another pattern: bring the table in
-        for (int i = tid; i < P.n_ent; i += THREADS) {
-            const int4 q = __ldg(reinterpret_cast<const int4 *>(P.ent) + i);
-            sval[i] = __hiloint2double(q.y, q.x);
-            soff[i] = q.z;
-        }
-        for (int i = tid; i < P.n_pat; i += THREADS) sdiag[i] = __ldg(P.pdiag + i);
-        for (int i = tid; i <= P.n_pat; i += THREADS) sstart[i] = __ldg(P.start + i);
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < RPT; s++) {
-            if (pid[s] > 0) {
-                const int row = r0 + s * THREADS + tid;
-                double sum = 0.0;
-                if (pid[s] != PAT_ESCAPE) {
-                    const int st = sstart[pid[s]], en = sstart[pid[s] + 1];
+        } else if (pid[s] != PAT_ESCAPE) {
+            // another pattern (boundary rows, a few per cent): walked straight from the table in global memory — a
+            // couple of KB that live in L1/L2 — by the lanes concerned only: no shared-memory copy, no CTA barrier
+            const int st = __ldg(P.start + pid[s]), en = __ldg(P.start + pid[s] + 1);
 #pragma unroll 1  // rare path: small code, the instruction cache belongs to the fast path
-                    for (int k = st; k < en; k++)
-                        sum = __dadd_rn(sum, __dmul_rn(sval[k], load_xd<COH, DIST>(x, row + soff[k], hs.halo_begin)));
-                    if (NEEDS_D && table_d) e[s].d = sdiag[pid[s]];
-                } else {
-                    const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
-#pragma unroll 1
-                    for (int k = lo; k < hi; k++)
-                        sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), load_xd<COH, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
-                    if (NEEDS_D) e[s].d = args.d[row];
-                }
-                contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row, strip_cta));
+            for (int k = st; k < en; k++) {
+                const int4 q = __ldg(reinterpret_cast<const int4 *>(P.ent) + k);
+                sum = __dadd_rn(sum, __dmul_rn(__hiloint2double(q.y, q.x), load_xd<COH, DIST>(x, row + q.z, hs.halo_begin)));
             }
+            if (NEEDS_D && table_d) e[s].d = __ldg(P.pdiag + pid[s]);
+        } else {
+            const int lo = A.rowptr[row], hi = A.rowptr[row + 1];
+#pragma unroll 1
+            for (int k = lo; k < hi; k++)
+                sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), load_xd<COH, DIST>(x, __ldg(A.col + k), hs.halo_begin)));
+            if (NEEDS_D) e[s].d = args.d[row];
         }
+        // reduction contributions are added in row order within the thread: a fixed tree
+        contrib = __dadd_rn(contrib, epi_store<EPI, DIST>(args, e[s], sum, y, row, strip_cta));
     }
     if (pushes<EPI, DIST>(args, strip_cta)) {
 #pragma unroll 1
@@ -134,11 +157,17 @@ int launch_cfg(const sparsh_matrix_s *A, const double *x, double *y, const EpiAr
         return SPARSH_ERR_INVALID;
     }
     const PatView P = A->pattern(args.d != nullptr && args.d == A->diag);
-    const size_t smem = (size_t)A->n_pent * 12 + (size_t)A->n_pat * 8 + (size_t)(A->n_pat + 1) * 4;  // <= 27 KB
+    // prefetch distance = CTAs of this kernel that are resident at a time (SPARSH_PAT2_PF overrides; 0 switches it off)
+    static const int pf = [] {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false>, THREADS, 0);
+        const char *e = getenv("SPARSH_PAT2_PF");
+        return e ? atoi(e) : ctx().sm_count * std::max(per_sm, 1);
+    }();
     if (d.dist)
-        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs);
+        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, true><<<grid, THREADS, 0, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf);
     else
-        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs);
+        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false><<<grid, THREADS, 0, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf);
     count_launch();
     SP_CUDA(cudaGetLastError());
     if (EpiTraits<EPI>::reduces) return launch_finalize_partials(grid, args.red_out);
@@ -157,6 +186,14 @@ int lean_rpt() {
 
 template <int LEN0, int EPI>
 int launch_len(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
+    // measured on B200, 3D Poisson 256^3 (profiles/r02g_pattern_lean_v3_sweep.log): the sweeps with a division in the
+    // epilogue (Jacobi, SOR) are fastest with one row per thread (256 x 1: 0.111 ms), the others with two (128 x 2:
+    // SpMV 0.081 ms); SPARSH_PAT2_RPT / sparsh_matrix_force_kernel(KIND_PATTERN, threads) override for experiments
+    static const bool forced = getenv("SPARSH_PAT2_RPT") != nullptr;
+    if (!forced && !A->threads_forced) {
+        if (EPI == EPI_JACOBI || EPI == EPI_SOR) return launch_cfg<256, 1, LEN0, EPI>(A, x, y, args, d);
+        return launch_cfg<128, 2, LEN0, EPI>(A, x, y, args, d);
+    }
     const int rpt = lean_rpt();
     if (A->threads == 128) {
         if (rpt == 1) return launch_cfg<128, 1, LEN0, EPI>(A, x, y, args, d);

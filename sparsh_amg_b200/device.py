@@ -109,6 +109,14 @@ class DeviceMatrix:
         check(self.lib.sparsh_matrix_kernel(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def kernel_name(self, epilogue):
+        """name of the kernel instantiation launched for `epilogue` ('spmv' | 'residual' | 'jacobi' | 'prolong' | 'sor' |
+        'spmv_dot' | 'resnorm')"""
+        epi = ["spmv", "residual", "jacobi", "prolong", "sor", "spmv_dot", "resnorm"].index(epilogue)
+        buf = C.create_string_buffer(200)
+        check(self.lib.sparsh_matrix_kernel_name(self.h, epi, buf, 200))
+        return buf.value.decode()
+
     def force_kernel(self, kind, threads_or_lanes):
         check(self.lib.sparsh_matrix_force_kernel(self.h, kind, threads_or_lanes))
         return self

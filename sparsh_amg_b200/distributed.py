@@ -107,12 +107,20 @@ class DistHierarchy:
         check(self.lib.sparsh_dist_level_matrix(self.h, level, C.byref(a)))
         return DeviceMatrix(handle=a.value, owned=False)
 
-    def pcg(self, b, x, tol, max_iter=1000):
+    def _solve(self, fn, b, x, tol, max_iter):
         hist = np.zeros(max_iter + 1)
         it = C.c_int()
-        rc = check(self.lib.sparsh_dist_pcg(self.h, b.ptr, x.ptr, float(tol), int(max_iter), dp(hist), C.byref(it)),
-                   allow_not_converged=True)
+        rc = check(fn(self.h, b.ptr, x.ptr, float(tol), int(max_iter), dp(hist), C.byref(it)), allow_not_converged=True)
         return it.value, hist[: it.value + 1], rc == capi.SPARSH_OK
+
+    def pcg(self, b, x, tol, max_iter=1000):
+        return self._solve(self.lib.sparsh_dist_pcg, b, x, tol, max_iter)
+
+    def amg_solve(self, b, x, tol, max_cycles=500):
+        return self._solve(self.lib.sparsh_dist_amg_solve, b, x, tol, max_cycles)
+
+    def pbicgstab(self, b, x, tol, max_iter=1000):
+        return self._solve(self.lib.sparsh_dist_pbicgstab, b, x, tol, max_iter)
 
 
 def init_comm(torch_dist, rank, world, device):

@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <iostream>
 #include <memory>
 #include <numeric>
 #include <vector>
@@ -374,3 +376,92 @@ void *sparsh_host_dist_upload(void *plv) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU entry points in the style of the reference's AMG.hpp solvers (the reference itself is single-GPU:
+// src/AMG_gpu_phases_2.cu).  Every rank — one process per GPU — calls with the SAME global A, b, x it would hand to
+// Solver_PCG_1, plus its rank, the number of ranks and the 128-byte id that rank 0 obtained from
+// sparsh_dist_get_unique_id and passed on (MPI_Bcast, a file, ...).  The hierarchy is built by the host setup on every
+// rank, the rank's row blocks are uploaded, the solve runs on the N GPUs, and x returns the GLOBAL solution on every rank.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+enum DistMethod { D_AMG = 0, D_PCG = 1, D_PBICG = 2 };
+
+void dist_driver(sp_matrix_mg &A, double *b, double *x, DistMethod m, int nranks, int rank, const char *id128, const char *label) {
+    const sparsh::Options &o = options();
+    auto check = [&](int rc, const char *what) {
+        if (rc != SPARSH_OK) {
+            std::fprintf(stderr, "sparsh_amg: %s (%s) failed (%d): %s\n", label, what, rc, sparsh_last_error());
+            std::exit(1);  // as the single-GPU entry points: loudly, never by falling back to the CPU
+        }
+    };
+    check(sparsh_init(o.device >= 0 ? o.device : rank), "sparsh_init");
+    check(sparsh_dist_init(id128, nranks, rank), "sparsh_dist_init");
+    const double t1 = omp_get_wtime();
+    AMG_GPU1_solver *S = new AMG_GPU1_solver();
+    S->AMG_solver_setup_jacobi(A);
+    void *plan = sparsh_host_dist_plan(S, nranks, rank, o.tail_threshold);
+    if (!plan) {
+        std::fprintf(stderr, "sparsh_amg: %s: single-level hierarchy, nothing to distribute (use the single-GPU entry point)\n", label);
+        std::exit(1);
+    }
+    sparsh_dist_t dh = (sparsh_dist_t)sparsh_host_dist_upload(plan);
+    if (!dh) std::exit(1);
+    const int *rows = nullptr;
+    const int nl = sparsh_host_dist_plan_rows(plan, 0, &rows);
+    const int n = A.nrow;
+    std::vector<double> bl((size_t)nl), xl((size_t)nl);
+    for (int i = 0; i < nl; i++) {
+        bl[i] = b[rows[i]];
+        xl[i] = x[rows[i]];
+    }
+    double *db = nullptr, *dx = nullptr;
+    check(sparsh_malloc(sizeof(double) * ((size_t)nl + 2), (void **)&db), "malloc");
+    check(sparsh_malloc(sizeof(double) * ((size_t)nl + 2), (void **)&dx), "malloc");
+    const double t2 = omp_get_wtime();
+    check(sparsh_memcpy_h2d(db, bl.data(), sizeof(double) * (size_t)nl), "h2d");
+    check(sparsh_memcpy_h2d(dx, xl.data(), sizeof(double) * (size_t)nl), "h2d");
+    double tol = o.tol;
+    if (o.tol_mode != sparsh::TOL_ABSOLUTE) {  // ||b|| of the GLOBAL right-hand side: every rank holds it
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += b[i] * b[i];
+        tol = o.tol * std::sqrt(s);
+    }
+    std::vector<double> hist((size_t)o.max_iter + 2, 0.0);
+    int it = 0;
+    int rc = m == D_AMG   ? sparsh_dist_amg_solve(dh, db, dx, tol, o.max_iter, hist.data(), &it)
+             : m == D_PCG ? sparsh_dist_pcg(dh, db, dx, tol, o.max_iter, hist.data(), &it)
+                          : sparsh_dist_pbicgstab(dh, db, dx, tol, o.max_iter, hist.data(), &it);
+    if (rc != SPARSH_OK && rc != SPARSH_ERR_NOT_CONVERGED) check(rc, "solve");
+    check(sparsh_memcpy_d2h(xl.data(), dx, sizeof(double) * (size_t)nl), "d2h");
+    const double t3 = omp_get_wtime();
+    check(sparsh_dist_allgather_rows(xl.data(), rows, nl, x, n), "gather");
+    sparsh::Report &r = sparsh::last_report();
+    r.iterations = it;
+    r.converged = rc == SPARSH_OK;
+    r.history.assign(hist.begin(), hist.begin() + it + 1);
+    r.solve_seconds = t3 - t2;
+    if (o.print_solve && rank == 0) {
+        for (int k = 1; k <= it; k++) std::cout << k << "\t" << hist[k] << "\n";
+        std::cout << label << " Setup Phase Time\t" << t2 - t1 << "\n";
+        std::cout << label << " Solve Phase Time\t" << t3 - t2 << "\n";
+    }
+    sparsh_free(db);
+    sparsh_free(dx);
+    sparsh_host_dist_plan_free(plan);  // destroys the distributed device hierarchy too
+    delete S;
+}
+
+}  // namespace
+
+void AMG_Solver_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128) {
+    dist_driver(A, b, x, D_AMG, nranks, rank, id128, "AMG (multi-GPU)");
+}
+void Solver_PCG_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128) {
+    dist_driver(A, b, x, D_PCG, nranks, rank, id128, "PCG (multi-GPU)");
+}
+void Solver_PBiCG_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128) {
+    dist_driver(A, b, x, D_PBICG, nranks, rank, id128, "PBiCGStab (multi-GPU)");
+}
+

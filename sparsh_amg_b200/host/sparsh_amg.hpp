@@ -84,6 +84,8 @@ struct Options {
     int max_iter = 10000;          // iteration cap (the reference's AMG and BiCGStab loops have none)
     int use_graph = 1;             // CUDA-graph the V-cycle / Krylov iteration
     int halo_mode = 1;             // multi-GPU halo exchange: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv
+    int device = -1;               // multi-GPU entry points: CUDA device of this rank (-1: the rank itself)
+    int tail_threshold = 1100000;  // multi-GPU: levels with at most this many rows are replicated on every GPU
     int gmres_restart = 30;        // Solver_GMRES_1 / Solver_PGMRES_1 (used by sparsh_gmres; the host-buffer path uses 30)
     double sa_theta = 0.08;        // COARSEN_SA: strength threshold (halved per level)
     double sa_relax = 4.0 / 3.0;   // COARSEN_SA: prolongator smoothing factor, omega = sa_relax / rho(D^-1 A)
@@ -246,5 +248,12 @@ void coarsening_2(sp_matrix_mg &A, double *&b, double *&x);
 // additions: restarted GMRES(options().gmres_restart), plain and V-cycle-preconditioned
 void Solver_GMRES_1(sp_matrix_mg &A, double *&b, double *&x);
 void Solver_PGMRES_1(sp_matrix_mg &A, double *&b, double *&x);
+// additions: the same solvers row-sharded over N GPUs of one node, one process per GPU (host/dist_plan.cpp).  Every rank
+// passes the same global A, b, x, its rank, the world size and the 128-byte id rank 0 got from sparsh_dist_get_unique_id;
+// x returns the global solution on every rank.  options().device (-1: = rank) selects the GPU,
+// options().tail_threshold the row count below which levels are replicated instead of partitioned.
+void AMG_Solver_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128);
+void Solver_PCG_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128);
+void Solver_PBiCG_MG(sp_matrix_mg &A, double *&b, double *&x, int nranks, int rank, const char *id128);
 
 #endif  // SPARSH_AMG_HPP_

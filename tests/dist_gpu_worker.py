@@ -61,10 +61,27 @@ def main():
     # second solve replays the captured graphs and must reproduce the first bit for bit
     it2, hist2, _ = dH.pcg(sp.DeviceVector(data=b[rows]), dxl.fill(0.0), tol, 500)
     assert it2 == it and np.array_equal(hist2, hist)
+    # the other entry points on the same handle: AMG as a solver and AMG-preconditioned BiCGStab against their
+    # single-GPU twins (same arithmetic per row; only the dot products / norms see another summation tree)
+    dxa = sp.DeviceVector(n).fill(0.0)
+    ita1, hista1, oka1 = dH1.amg_solve(sp.DeviceVector(data=b), dxa, tol, 200)
+    ita, hista, oka = dH.amg_solve(sp.DeviceVector(data=b[rows]), dxl.fill(0.0), tol, 200)
+    assert oka and oka1 and ita == ita1, (ita, ita1)
+    np.testing.assert_allclose(hista, hista1, rtol=1e-10, atol=1e-13 * hista1[0])
+    np.testing.assert_allclose(dxl.download(), dxa.download()[rows], rtol=1e-8, atol=1e-10 * np.abs(x1).max())
+    dxb = sp.DeviceVector(n).fill(0.0)
+    itb1, histb1, okb1 = dH1.pbicgstab(sp.DeviceVector(data=b), dxb, tol, 500)
+    itb, histb, okb = dH.pbicgstab(sp.DeviceVector(data=b[rows]), dxl.fill(0.0), tol, 500)
+    assert okb and okb1 and abs(itb - itb1) <= 1, (itb, itb1)
+    mb = min(len(histb), len(histb1))
+    np.testing.assert_allclose(histb[:mb], histb1[:mb], rtol=1e-7, atol=1e-12 * histb1[0])  # BiCGStab amplifies rounding
+    # and PCG once more after the other solvers' graphs were captured: still the same bits
+    it3, hist3, _ = dH.pcg(sp.DeviceVector(data=b[rows]), dxl.fill(0.0), tol, 500)
+    assert it3 == it and np.array_equal(hist3, hist)
     dist.barrier()
     if rank == 0:
-        print(f"DIST_GPU_OK world={world} grid={grid} nd={plan.nd}/{plan.nlevels} iterations={it} (1-GPU {it1}) "
-              f"halo_mode={halo_mode} graph={use_graph}")
+        print(f"DIST_GPU_OK world={world} grid={grid} nd={plan.nd}/{plan.nlevels} pcg={it} (1-GPU {it1}) amg={ita} ({ita1}) "
+              f"bicgstab={itb} ({itb1}) halo_mode={halo_mode} graph={use_graph}")
     from sparsh_amg_b200.distributed import shutdown
 
     shutdown(dist, plan)

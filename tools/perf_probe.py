@@ -67,7 +67,7 @@ def main():
     if args.families == "all":
         fams += [("dict256", 3, 256), ("dict128", 3, 128), ("stream256", 1, 256), ("stream128", 1, 128),
                  ("vector4", 2, 4), ("scalar", 0, 256)]
-        if os.environ.get("SPARSH_PATTERN", "0") in ("1", "2"):
+        if os.environ.get("SPARSH_PATTERN", "1") in ("1", "2"):
             fams[1:1] = [("pattern128", 4, 128), ("pattern256", 4, 256)]
     for name, kind, tl in fams:
         if kind is not None:
