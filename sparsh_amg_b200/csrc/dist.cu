@@ -573,7 +573,11 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
     // A generic push (first sweep after a transfer, residual -> R, x -> P, p -> A p) runs on the auxiliary stream BESIDE
     // the consuming grid, not in front of it: it waits for the neighbours' acks and feeds THEIR strips; this rank's grid
     // does not depend on it (its own strips wait for the neighbours' flags), so only the join does.
-    if (need_push) {
+    // (Unless the grid itself carries a fused push of its output: producer-side sequence numbers of one operator are
+    // taken from a single device counter, so its two producers — the generic push and the fused one — must not overlap.)
+    const bool beside = need_push && hs.nsend == 0;
+    if (need_push && !beside) SP_TRY(peer_push(h, op, x));
+    if (beside) {
         SP_TRY(fork_aux());
         StreamSwap sw(m.comm_stream);
         SP_TRY(peer_push(h, op, x));
@@ -584,7 +588,7 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
     else
         rc = launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
     SP_TRY(rc);
-    if (need_push) SP_TRY(join_aux());
+    if (beside) SP_TRY(join_aux());
     return SPARSH_OK;
 }
 

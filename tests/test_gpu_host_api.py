@@ -210,6 +210,85 @@ def test_full_size_config4_27pt_diffusion_192_bicgstab(host):
     host.set_options(threads=8, relax=0.66667)
 
 
+def _host_levels(amg):
+    """host hierarchy -> the level dictionaries DeviceHierarchy / the oracle take"""
+    from oracle_bindings import CSR
+
+    levels = []
+    for L in amg.levels():
+        A, P = L["A"], L["P"]
+        levels.append(dict(A=CSR(A.nrow, A.ncol, A.rowptr.copy(), A.colindex.copy(), A.val.copy()), diag=np.array(L["diag"]),
+                           P=None if P is None else CSR(P.nrow, P.ncol, P.rowptr.copy(), P.colindex.copy(), P.val.copy())))
+    return levels
+
+
+def test_config4_sa_bicgstab_small_parity_with_oracle(host, oracle):
+    """BASELINE config 4 as written — SMOOTHED-AGGREGATION hierarchy + AMG-preconditioned BiCGStab — on the 27-point
+    operator at 32^3 and 48^3: the device path against the CPU oracle running the same hierarchy (general P with 3-4
+    entries per row, coarse operators with 50-90 nnz/row: the kernels that are NOT compressible)."""
+    import sparsh_amg_b200 as sp
+    from oracle_bindings import Hierarchy, OracleAmg
+
+    counts = {}
+    for g in (32, 48):
+        host.set_options(coarsening=2, relax=0.4, coarse_upper=500, coarse_lower=100, max_levels=32)
+        D = host.HostMatrix.diffusion27(g, g, g)
+        amg = host.HostAmg(D)
+        levels = _host_levels(amg)
+        assert amg.nlevels >= 3
+        b = D.times(np.random.default_rng(42).random(D.nrow))
+        tol = 1e-8 * np.linalg.norm(b)
+        oa = OracleAmg(hierarchy=Hierarchy(levels))
+        oa.set_smoother(0.4, 6)
+        dH = sp.DeviceHierarchy(levels, omega=0.4)
+        assert dH.level(1)[0].kernel()[0] in (sp.capi.KIND_STREAM, sp.capi.KIND_VECTOR)  # no twin: plain CSR
+        db, dx = sp.DeviceVector(data=b), sp.DeviceVector(D.nrow)
+        _, want = oa.pbicgstab(b, np.zeros(D.nrow), tol, 400)
+        it, hist, ok = dH.pbicgstab(db, dx.fill(0.0), tol, 400)
+        assert ok and abs(it - (len(want) - 1)) <= 1, (it, len(want) - 1)
+        assert_hist(hist, want, rtol=1e-7)
+        assert np.linalg.norm(b - D.times(dx.download())) <= 1.5 * tol
+        counts[g] = it
+        amg.free()
+        D.free()
+    host.set_options(coarsening=0, relax=0.66667, coarse_upper=4000, coarse_lower=2000)
+    assert counts[32] <= 35 and counts[48] <= 50, counts  # oracle: 29 and 41 (strong anisotropy, omega = 0.4)
+
+
+def test_full_size_config4_sa_hierarchy_192_bicgstab(host):
+    """BASELINE config 4 at full size AS WRITTEN: 27-point variable-coefficient anisotropic diffusion 192^3 (7.1M rows,
+    189M nnz), smoothed-aggregation hierarchy (host/setup.cpp: SA_Prolongator; the reference advertises it, README.md:10,
+    and has no code for it: SURVEY F2), AMG-preconditioned BiCGStab.  No CPU oracle finishes this size in seconds:
+    convergence to rel 1e-8, true residual, iteration count in the range the oracle-checked 32^3 / 48^3 runs show,
+    bit-reproducibility, SpMV at full size against a host row sum."""
+    import sparsh_amg_b200 as sp
+
+    host.set_options(threads=32, coarsening=2, relax=0.4, max_levels=32)
+    A = host.HostMatrix.diffusion27(192, 192, 192)
+    amg = host.HostAmg(A)
+    assert 3 <= amg.nlevels <= 8 and amg.level_dims(amg.nlevels - 1)[0] <= 4000
+    dH = amg.upload()
+    n = A.nrow
+    A0, P0, _ = dH.level(0)
+    assert A0.kernel()[0] == sp.capi.KIND_STREAM and A0.kernel()[1] == 128   # 27 nnz/row, distinct values: plain CSR
+    assert P0.nnz > 3 * n                                                     # smoothed P: several entries per row
+    x = np.random.default_rng(5).standard_normal(n)
+    np.testing.assert_array_equal(A0.spmv(sp.DeviceVector(data=x)).download(), A.times(x))
+    b = A.times(np.random.default_rng(42).random(n))  # b = A x*, x* ~ U(0,1), seed 42 (SURVEY 8d)
+    db, dx = sp.DeviceVector(data=b), sp.DeviceVector(n).fill(0.0)
+    tol = 1e-8 * np.linalg.norm(b)
+    it, hist, ok = dH.pbicgstab(db, dx, tol, 500)
+    assert ok and 20 <= it <= 400, (it, hist[-1] / hist[0])  # 29 / 41 at 32^3 / 48^3: grows with the grid
+    xs = dx.download()
+    assert np.linalg.norm(b - A.times(xs)) <= 1.5 * tol
+    it2, hist2, _ = dH.pbicgstab(db, dx.fill(0.0), tol, 500)
+    assert it2 == it and np.array_equal(hist, hist2)
+    np.testing.assert_array_equal(dx.download(), xs)
+    amg.free()
+    A.free()
+    host.set_options(threads=8, coarsening=0, relax=0.66667)
+
+
 def test_config4_small_parity_with_oracle(host, oracle):
     """the same 27-point operator at 32^3 against the CPU oracle: same BiCGStab / PCG iteration counts and histories"""
     import sparsh_amg_b200 as sp
