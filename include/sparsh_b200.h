@@ -103,6 +103,10 @@ int sparsh_pattern_encode(int nrow, int ncol, int nnz, const int *h_rowptr, cons
                           const double *h_val, const double *h_diag, unsigned char *pat, double *ent_val,
                           int *ent_off, int *start, int *n_pat, int *n_escape);
 
+/* what the upload built (the encoder runs on the DEVICE there; it must agree with sparsh_pattern_encode): number of
+ * patterns (0: no twin), table entries, escape rows, fraction of the rows that carry pattern 0 */
+int sparsh_matrix_pattern_stats(sparsh_matrix_t A, int *n_pat, int *n_ent, int *n_escape, double *cover0);
+
 /* x windows of the TMA-staged csr-pattern8 kernel (host-only helper, so the tiling arithmetic can be checked without a
  * GPU): a tile of *tile consecutive rows gathers x only from *nwin contiguous ranges [r0 + lo[w], r0 + lo[w] + len[w]),
  * one per group of table offsets that lie within a tile length of each other; win[k] names the window of table entry k,

@@ -14,8 +14,8 @@
 //     when done (fused compute + communication over peer memory).  Sequence counters live in device memory, so all of
 //     it replays inside a CUDA graph: no NCCL call, host round trip or staging copy sits on the exchange path;
 //   * halo_mode 0: pack kernel -> grouped ncclSend/ncclRecv into the halo tail on a communication stream (fallback);
-//     Boundary strips and interior rows are ONE launch: the strip CTAs carry the lowest block indices (scheduled first),
-//     wait for the flags and signal as soon as the last of them is done; the interior CTAs behind them never wait;
+//     Boundary strips run beside the interior rows (auxiliary high-priority stream; or, SPARSH_DIST_MERGE=1, as the first
+//     CTAs of one grid): they wait for the flags and signal as soon as the last of them is done; interior rows never wait;
 //   * Krylov scalars: local fixed-tree partial, then a one-warp kernel stores it into a slot of every peer's arena,
 //     waits for the peers' slots and adds them in rank order (deterministic, graph-replayable; ~one NVLink round trip).
 //     The handshake error flag rides along, so every rank learns of a failure in the same iteration;
@@ -512,9 +512,10 @@ bool env_on(const char *name, bool dflt) {
 
 // y = epi(op x).  The rows that touch the halo (and, for the fused Jacobi, the rows a neighbour needs) form the two
 // boundary strips, everything else is interior.  Peer mode: a generic push first if the halo of x is not already on
-// its way, then ONE launch — the strip CTAs come first in the grid, wait for the flags, compute, optionally store the
-// new values into the neighbours and signal as soon as the last of them is done, while the interior CTAs of the same
-// grid never wait.  `push_output`: y is the next input of this same operator.
+// its way, then the strips — their CTAs wait for the flags, compute, optionally store the new values into the
+// neighbours and signal as soon as the last of them is done — beside the interior rows, which never wait: as two
+// launches on two streams (default) or as one grid whose first CTAs are the strips.  `push_output`: y is the next
+// input of this same operator.
 int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, EpiArgs args, bool push_output = false) {
     if (!op.needs_exchange()) return launch_csr(op.M, epi, x, y, args, 0, op.nrow);
     const bool reduces = epi == EPI_SPMV_DOT || epi == EPI_RESNORM;
@@ -557,7 +558,12 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
         hs.seq = h->seq + op.id;
         h->halo_ready[by] = op.id + 1;
     }
-    static const bool merge = env_on("SPARSH_DIST_MERGE", true);
+    // Default: boundary strips (with the push in front of them) on the high-priority auxiliary stream, interior rows as a
+    // launch of their own on the main stream.  Measured on B200, 256^3 (profiles/r02i_n2_*.json, r02j_*.json): 0.1009 s
+    // against 0.1058 s for the single launch at N=2, 0.0815 / 0.0827 at N=4, 0.0727 / 0.0723 at N=8 — the fork/join
+    // costs nothing measurable inside a CUDA graph, the extra launch is hidden behind the interior rows, and the
+    // neighbours hear from the strips earlier.  SPARSH_DIST_MERGE=1 selects the single launch.
+    static const bool merge = env_on("SPARSH_DIST_MERGE", false);
     if (!merge && split && !reduces) {
         EpiArgs iargs = args;  // interior rows: nothing to send
         iargs.pm_ptr = nullptr;
@@ -570,26 +576,12 @@ int apply(sparsh_dist_s *h, const DistOp &op, int epi, double *x, double *y, Epi
         SP_TRY(launch_csr(op.M, epi, x, y, iargs, op.ib, op.ie));
         return join_aux();
     }
-    // A generic push (first sweep after a transfer, residual -> R, x -> P, p -> A p) runs on the auxiliary stream BESIDE
-    // the consuming grid, not in front of it: it waits for the neighbours' acks and feeds THEIR strips; this rank's grid
-    // does not depend on it (its own strips wait for the neighbours' flags), so only the join does.
-    // (Unless the grid itself carries a fused push of its output: producer-side sequence numbers of one operator are
-    // taken from a single device counter, so its two producers — the generic push and the fused one — must not overlap.)
-    const bool beside = need_push && hs.nsend == 0;
-    if (need_push && !beside) SP_TRY(peer_push(h, op, x));
-    if (beside) {
-        SP_TRY(fork_aux());
-        StreamSwap sw(m.comm_stream);
-        SP_TRY(peer_push(h, op, x));
-    }
-    int rc;
-    if (!split)
-        rc = launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
-    else
-        rc = launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
-    SP_TRY(rc);
-    if (beside) SP_TRY(join_aux());
-    return SPARSH_OK;
+    // one launch: the generic push (if any) first — a consumer grid whose strip CTAs fill the GPU while they wait must
+    // never be in front of the push that the neighbours' strips are waiting for (that is a cross-GPU deadlock: measured
+    // at 512^3, where a strip has more CTAs than the GPU holds) — then strips + interior rows as one grid
+    if (need_push) SP_TRY(peer_push(h, op, x));
+    if (!split) return launch_csr3(op.M, epi, x, y, args, 0, op.nrow, 0, 0, 0, 0, &hs);
+    return launch_csr3(op.M, epi, x, y, args, 0, op.ib, op.ie, op.nrow, op.ib, op.ie, &hs);
 }
 
 PeerTab peer_tab(const sparsh_dist_s *h) {

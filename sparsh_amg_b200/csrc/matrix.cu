@@ -1,6 +1,7 @@
 // matrix.cu — device CSR upload, kernel-family selection, and the per-op entry points of the C-ABI.
 // Replaces class sp_matrix_gpu (reference include/AMG_gpu_matrix.hpp:10-48, src/AMG_gpu_matrix.cu:26-142).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -173,8 +174,6 @@ bool dict_encode(int n, const int *rp, const int *ci, const double *v, unsigned 
 
 // encodes and uploads; false (nothing uploaded) when the matrix is not representable or SPARSH_DICT=0
 bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v) {
-    const char *env = getenv("SPARSH_DICT");
-    if (env && atoi(env) == 0) return false;
     const int n = A->nrow;
     const size_t nnz = (size_t)A->nnz;
     if (nnz == 0) return false;
@@ -341,6 +340,87 @@ bool pattern_windows(const std::vector<int> &off, PatWindows &W, std::vector<uns
     return true;
 }
 
+// ---- csr-pattern8 encoder on the device -----------------------------------------------------------------------
+// The host encoder above (kept as the CPU-checkable statement of the format, sparsh_pattern_encode) walks every row
+// with a hash map on one core: 0.5 s for 3D Poisson 256^3, a quarter of the whole upload.  The matrix is on the device
+// anyway by then, so: (1) one kernel hashes every row (same hash as row_pattern_hash) and registers it in a small
+// open-addressing table — key = hash, representative = smallest row index (atomicMin: the first occurrence, as on the
+// host), count —; (2) the host reads the few candidates back, orders them exactly like the host encoder (count
+// descending, first occurrence ascending) and builds the table from the representatives' rows; (3) a second kernel
+// gives every row its pattern id after comparing it ENTRY BY ENTRY with the tabulated pattern (a hash collision or a
+// differing smoothing diagonal makes the row an escape).  The result equals the host encoder's.
+constexpr int PAT_SLOTS = 1 << 17;   // open addressing
+constexpr int PAT_MAX_CAND = 1 << 15;  // distinct rows beyond which the matrix is declared not stencil-like
+struct PatSlot {
+    unsigned long long key;  // 0 = empty
+    int rep, count;
+};
+
+__device__ __forceinline__ unsigned long long device_row_hash(const int *rp, const int *ci, const double *v, int row) {
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(rp[row + 1] - rp[row]);
+    for (int k = rp[row]; k < rp[row + 1]; k++) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+        h = (h ^ bits) * 0x100000001B3ull;
+        h = (h ^ (unsigned long long)(unsigned int)(ci[k] - row)) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+    }
+    return h ? h : 1ull;
+}
+
+__global__ void __launch_bounds__(256)
+    pat_hash_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ v, PatSlot *table,
+                    int *slot_of, int *overflow) {
+    // overflow[0]: "rows do not repeat" (too many distinct rows) — everybody stops as soon as somebody finds out;
+    // overflow[1]: distinct rows registered so far
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    slot_of[row] = -1;
+    if (rp[row + 1] - rp[row] > PAT_MAX_ROW || *reinterpret_cast<volatile int *>(overflow) != 0) return;
+    const unsigned long long h = device_row_hash(rp, ci, v, row);
+    unsigned int s = (unsigned int)(h >> 20) & (PAT_SLOTS - 1);
+    for (int probe = 0; probe < 256; probe++, s = (s + 1) & (PAT_SLOTS - 1)) {  // load factor <= 1/4: probes are short
+        const unsigned long long seen = atomicCAS(&table[s].key, 0ull, h);
+        if (seen == 0ull && atomicAdd(overflow + 1, 1) >= PAT_MAX_CAND) break;
+        if (seen == 0ull || seen == h) {
+            atomicMin(&table[s].rep, row);
+            atomicAdd(&table[s].count, 1);
+            slot_of[row] = (int)s;
+            return;
+        }
+    }
+    atomicExch(overflow, 1);
+}
+
+// pat[i] = id of row i's pattern if the row equals the tabulated pattern entry by entry (and, when `diag` is given, its
+// smoothing diagonal equals the tabulated one bit for bit), PAT_ESCAPE otherwise; counts[0] += covered rows, counts[1] += rows
+// of pattern 0
+__global__ void __launch_bounds__(256)
+    pat_assign_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ v,
+                      const double *__restrict__ diag, const int *__restrict__ slot_of, const int *__restrict__ id_of_slot,
+                      const PatEntry *__restrict__ ent, const int *__restrict__ start, const double *__restrict__ pdiag,
+                      unsigned char *pat, unsigned long long *counts) {
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    int id = -1;
+    if (row < n) {
+        const int s = slot_of[row];
+        if (s >= 0) id = id_of_slot[s];
+        if (id >= 0) {
+            const int lo = rp[row], len = rp[row + 1] - lo, st = start[id];
+            bool same = len == start[id + 1] - st;
+            for (int k = 0; same && k < len; k++)
+                same = ci[lo + k] - row == ent[st + k].off && __double_as_longlong(v[lo + k]) == __double_as_longlong(ent[st + k].v);
+            if (same && diag) same = __double_as_longlong(diag[row]) == __double_as_longlong(pdiag[id]);
+            if (!same) id = -1;
+        }
+        pat[row] = (unsigned char)(id >= 0 ? id : PAT_ESCAPE);
+    }
+    const unsigned int covered = __ballot_sync(0xffffffffu, id >= 0), zero = __ballot_sync(0xffffffffu, id == 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (covered) atomicAdd(&counts[0], (unsigned long long)__popc(covered));
+        if (zero) atomicAdd(&counts[1], (unsigned long long)__popc(zero));
+    }
+}
+
 // SPARSH_PATTERN: 1 (default) build the twin and run the pattern kernel wherever it applies (measured on B200: fused
 // Jacobi sweep on 3D Poisson 256^3 0.111 ms against 0.179 ms for csr-dict16 and 0.294 ms for plain CSR, whole AMG-PCG
 // solve 0.157 s against 0.206 s; bit-identical results); 0 no twin; 2 build the twin but keep the dict / stream kernel
@@ -350,54 +430,130 @@ int pattern_mode() {
     return env ? atoi(env) : 1;
 }
 
-// encodes and uploads; false (nothing uploaded) when the rows do not repeat enough
+// encodes (on the device, see above) and keeps the twin; false (nothing kept) when the rows do not repeat enough.  rp,
+// ci, v are the HOST arrays (the table is built from the representatives' rows), the device copies are A->rowptr/col/val.
 bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, const double *h_diag) {
     const int n = A->nrow;
     if (n == 0 || A->nnz == 0) return false;
-    std::vector<unsigned char> pat((size_t)n + 16, (unsigned char)PAT_ESCAPE);
+    cudaStream_t st = ctx().stream;
+    PatSlot *d_table = nullptr;
+    int *d_slot_of = nullptr, *d_overflow = nullptr, *d_id_of = nullptr;
+    unsigned long long *d_counts = nullptr;
+    bool kept = false;
+    auto cleanup = [&]() {
+        cudaFree(d_table);
+        cudaFree(d_slot_of);
+        cudaFree(d_overflow);
+        cudaFree(d_id_of);
+        cudaFree(d_counts);
+        if (!kept) {
+            cudaFree(A->pat);
+            cudaFree(A->pat_ent);
+            cudaFree(A->pat_start);
+            cudaFree(A->pat_diag);
+            A->pat = nullptr;
+            A->pat_ent = nullptr;
+            A->pat_start = nullptr;
+            A->pat_diag = nullptr;
+        }
+        cudaGetLastError();
+    };
+    bool ok = cudaMalloc(&d_table, sizeof(PatSlot) * PAT_SLOTS) == cudaSuccess &&
+              cudaMalloc(&d_slot_of, sizeof(int) * (size_t)n) == cudaSuccess && cudaMalloc(&d_overflow, sizeof(int) * 2) == cudaSuccess &&
+              cudaMalloc(&d_id_of, sizeof(int) * PAT_SLOTS) == cudaSuccess &&
+              cudaMalloc(&d_counts, sizeof(unsigned long long) * 2) == cudaSuccess;
+    if (!ok) {
+        cleanup();
+        return false;
+    }
+    std::vector<PatSlot> table(PAT_SLOTS, PatSlot{0ull, 0x7fffffff, 0});
+    cudaMemcpyAsync(d_table, table.data(), sizeof(PatSlot) * PAT_SLOTS, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_overflow, 0, sizeof(int) * 2, st);
+    cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * 2, st);
+    const int grid = (n + 255) / 256;
+    pat_hash_kernel<<<grid, 256, 0, st>>>(n, A->rowptr, A->col, A->val, d_table, d_slot_of, d_overflow);
+    int overflow = 0;
+    cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || overflow) {
+        cleanup();
+        return false;
+    }
+    if (cudaMemcpy(table.data(), d_table, sizeof(PatSlot) * PAT_SLOTS, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cleanup();
+        return false;
+    }
+    // candidates in the host encoder's order: by decreasing row count, ties by first occurrence
+    struct Cand {
+        int rep, count, slot;
+    };
+    std::vector<Cand> cand;
+    for (int sidx = 0; sidx < PAT_SLOTS; sidx++)
+        if (table[sidx].key != 0ull) cand.push_back(Cand{table[sidx].rep, table[sidx].count, sidx});
+    if (cand.empty()) {
+        cleanup();
+        return false;
+    }
+    std::sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b) { return a.count != b.count ? a.count > b.count : a.rep < b.rep; });
     PatternTable T;
-    if (!pattern_encode(n, rp, ci, v, h_diag, pat.data(), T, 0.75)) return false;
+    T.start.push_back(0);
+    std::vector<int> id_of(PAT_SLOTS, -1);
+    for (const Cand &c : cand) {
+        const int r = c.rep, len = rp[r + 1] - rp[r];
+        if ((int)T.diag.size() == PAT_ESCAPE) break;
+        if ((int)T.val.size() + len > PAT_MAX_ENT) continue;
+        id_of[c.slot] = (int)T.diag.size();
+        double d = 0.0;
+        bool found = false;
+        for (int k = rp[r]; k < rp[r + 1]; k++) {
+            T.val.push_back(v[k]);
+            T.off.push_back(ci[k] - r);
+            if (!found && ci[k] == r) {
+                d = v[k];
+                found = true;
+            }
+        }
+        T.diag.push_back(d);
+        T.start.push_back((int)T.val.size());
+    }
     const int n_pat = (int)T.diag.size(), n_ent = (int)T.val.size();
+    if (n_pat == 0) {
+        cleanup();
+        return false;
+    }
     std::vector<PatEntry> ent((size_t)n_ent + 8, PatEntry{0.0, 0, 0});
     for (int k = 0; k < n_ent; k++) ent[k] = PatEntry{T.val[k], T.off[k], 0};
-    cudaStream_t st = ctx().stream;
-    bool ok = cudaMalloc(&A->pat, pat.size()) == cudaSuccess &&
-              cudaMalloc(&A->pat_ent, sizeof(PatEntry) * ent.size()) == cudaSuccess &&
-              cudaMalloc(&A->pat_start, sizeof(int) * ((size_t)n_pat + 1)) == cudaSuccess &&
-              cudaMalloc(&A->pat_diag, sizeof(double) * (size_t)n_pat) == cudaSuccess;
+    ok = cudaMalloc(&A->pat, (size_t)n + 16) == cudaSuccess && cudaMalloc(&A->pat_ent, sizeof(PatEntry) * ent.size()) == cudaSuccess &&
+         cudaMalloc(&A->pat_start, sizeof(int) * ((size_t)n_pat + 1)) == cudaSuccess &&
+         cudaMalloc(&A->pat_diag, sizeof(double) * (size_t)n_pat) == cudaSuccess;
+    unsigned long long counts[2] = {0ull, 0ull};
     if (ok) {
-        cudaMemcpyAsync(A->pat, pat.data(), pat.size(), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(A->pat, PAT_ESCAPE, (size_t)n + 16, st);
         cudaMemcpyAsync(A->pat_ent, ent.data(), sizeof(PatEntry) * ent.size(), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(A->pat_start, T.start.data(), sizeof(int) * ((size_t)n_pat + 1), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(A->pat_diag, T.diag.data(), sizeof(double) * (size_t)n_pat, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_id_of, id_of.data(), sizeof(int) * PAT_SLOTS, cudaMemcpyHostToDevice, st);
+        // rows whose smoothing diagonal (A->diag, uploaded from h_diag) differs from the tabulated one become escapes
+        pat_assign_kernel<<<grid, 256, 0, st>>>(n, A->rowptr, A->col, A->val, h_diag ? A->diag : nullptr, d_slot_of, d_id_of, A->pat_ent,
+                                                A->pat_start, A->pat_diag, A->pat, d_counts);
+        cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, st);
         ok = cudaStreamSynchronize(st) == cudaSuccess;
     }
-    if (!ok) {
-        cudaFree(A->pat);
-        cudaFree(A->pat_ent);
-        cudaFree(A->pat_start);
-        cudaFree(A->pat_diag);
-        A->pat = nullptr;
-        A->pat_ent = nullptr;
-        A->pat_start = nullptr;
-        A->pat_diag = nullptr;
-        cudaGetLastError();
+    if (!ok || (double)counts[0] < 0.75 * (double)n) {  // min_cover of the host encoder's upload path
+        cleanup();
         return false;
     }
     A->n_pat = n_pat;
     A->n_pent = n_ent;
-    A->n_escape = T.n_escape;
+    A->n_escape = n - (int)counts[0];
     A->pat_far = 0;
     for (int k = 0; k < n_ent; k++) A->pat_far = std::max(A->pat_far, T.off[k]);
     {  // pattern 0 by value for the lean kernel (spmv.cu: csr_pat2_kernel)
         Pat0 z;
         const int len0 = T.start[1] - T.start[0];
-        long long rows0 = 0;
-        for (int i = 0; i < n; i++) rows0 += pat[i] == 0;
         if (len0 >= 1 && len0 <= PAT0_MAX) {
             z.len = len0;
             z.diag = T.diag[0];
-            z.cover = (double)rows0 / (double)n;
+            z.cover = (double)counts[1] / (double)n;
             z.lo = z.hi = T.off[0];
             for (int k = 0; k < len0; k++) {
                 z.off[k] = T.off[k];
@@ -421,6 +577,8 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
         }
     }
     A->has_pat = true;
+    kept = true;
+    cleanup();
     return true;
 }
 
@@ -441,30 +599,45 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
                          const double *h_val, const double *h_diag, sparsh_matrix_t *out) {
     SP_TRY(ensure_init());
     SP_REQUIRE(out != nullptr, "out is NULL");
+    static const bool timing = getenv("SPARSH_UPLOAD_TIMING") != nullptr;  // developer switch: where does the upload go?
+    const auto t0 = std::chrono::steady_clock::now();
     SP_TRY(validate(nrow, ncol, nnz, h_rowptr, h_colindex));
     sparsh_matrix_s *A = new sparsh_matrix_s();
     A->nrow = nrow;
     A->ncol = ncol;
     A->nnz = nnz;
+    auto lap = [&](const char *what) {
+        if (timing && nnz > 1000000)
+            std::fprintf(stderr, "[upload %d x %d, %d nnz] %s at %.3f s\n", nrow, ncol, nnz, what,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    lap("validated");
     choose_kernel(A, h_rowptr);
+    lap("row statistics");
     int rc = upload(A, h_rowptr, h_colindex, h_val, h_diag);
     if (rc != SPARSH_OK) {
         sparsh_matrix_destroy(A);
         return rc;
     }
-    // matrices that would run the stream kernel get the compressed twin when their dictionaries fit
-    if (A->kind == KIND_STREAM && build_dict(A, h_rowptr, h_colindex, h_val)) {
+    lap("CSR copied");
+    // Matrices that would run the stream kernel get a lossless compressed twin when they are stencil-like.
+    // csr-pattern8 first (1 B per row, encoded on the device): when the rows repeat it wins, and the csr-dict16 twin
+    // (2 B per entry, encoded by the host: 0.5 s per 10^8 entries) is not even built unless SPARSH_DICT=2 asks for both.
+    const int pmode = pattern_mode();
+    const char *denv = getenv("SPARSH_DICT");
+    const int dmode = denv ? atoi(denv) : 1;  // 0: never, 1: when csr-pattern8 is not selected, 2: always (tests, A/B runs)
+    // (rectangular operators qualify too: the multi-GPU local blocks are nrow x (owned + halo) with a diagonal)
+    bool pattern_selected = false;
+    if (pmode > 0 && A->kind == KIND_STREAM && build_pattern(A, h_rowptr, h_colindex, h_val, h_diag)) pattern_selected = pmode == 1;
+    if (A->kind == KIND_STREAM && dmode > 0 && (!pattern_selected || dmode == 2) && build_dict(A, h_rowptr, h_colindex, h_val)) {
         A->kind = KIND_DICT;
         A->threads = 128;  // measured on B200 (256^3 Jacobi): 128-thread CTAs x 4 rows per thread 0.180 ms, 256 x 4 0.199 ms
     }
-    // ... and the per-row pattern twin when rows repeat (SPARSH_PATTERN, see pattern_mode)
-    const int pmode = pattern_mode();
-    // (rectangular operators qualify too: the multi-GPU local blocks are nrow x (owned + halo) with a diagonal)
-    if (pmode > 0 && (A->kind == KIND_STREAM || A->kind == KIND_DICT) &&
-        build_pattern(A, h_rowptr, h_colindex, h_val, h_diag) && pmode == 1) {
+    if (pattern_selected) {
         A->kind = KIND_PATTERN;
         A->threads = 128;
     }
+    lap("twins built");
     *out = A;
     return SPARSH_OK;
 }
@@ -571,6 +744,16 @@ int sparsh_matrix_kernel(sparsh_matrix_t A, int *kind, int *threads_or_lanes, in
     if (smem_bytes) *smem_bytes = A->kind == KIND_STREAM ? A->smem_bytes : 0;
     if (smem_bytes && A->kind == KIND_DICT)
         *smem_bytes = ((((A->threads == 256 ? A->win256 : A->win128) + 16) + 7) & ~7) * 2 + A->n_dval * 8 + A->n_doff * 4;
+    return SPARSH_OK;
+}
+
+// statistics of the csr-pattern8 twin as the device encoder built it (n_pat == 0: no twin)
+int sparsh_matrix_pattern_stats(sparsh_matrix_t A, int *n_pat, int *n_ent, int *n_escape, double *cover0) {
+    SP_REQUIRE(A != nullptr, "matrix is NULL");
+    if (n_pat) *n_pat = A->has_pat ? A->n_pat : 0;
+    if (n_ent) *n_ent = A->has_pat ? A->n_pent : 0;
+    if (n_escape) *n_escape = A->has_pat ? A->n_escape : A->nrow;
+    if (cover0) *cover0 = A->has_pat ? A->pat0.cover : 0.0;
     return SPARSH_OK;
 }
 

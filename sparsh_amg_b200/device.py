@@ -109,6 +109,12 @@ class DeviceMatrix:
         check(self.lib.sparsh_matrix_kernel(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def pattern_stats(self):
+        """(patterns, table entries, escape rows, share of pattern 0) of the csr-pattern8 twin; patterns == 0: no twin"""
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        check(self.lib.sparsh_matrix_pattern_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def kernel_name(self, epilogue):
         """name of the kernel instantiation launched for `epilogue` ('spmv' | 'residual' | 'jacobi' | 'prolong' | 'sor' |
         'spmv_dot' | 'resnorm')"""

@@ -124,11 +124,50 @@ def test_fixture_matrix_keeps_plain_csr(sp, fixture_system):
         dA.force_kernel(sp.capi.KIND_DICT, 256)
 
 
+def _host_pattern_encode(sp, M, diag):
+    """the host statement of the csr-pattern8 encoder (sparsh_pattern_encode) -> (n_pat, n_ent, n_escape)"""
+    import ctypes as C
+
+    lib = sp.capi.load()
+    pat = np.zeros(M.nrow + 16, dtype=np.uint8)
+    ev, eo, st = np.zeros(2048), np.zeros(2048, dtype=np.int32), np.zeros(257, dtype=np.int32)
+    npat, nesc = C.c_int(), C.c_int()
+    dptr = sp.capi.dp(np.ascontiguousarray(diag, dtype=np.float64)) if diag is not None else None
+    sp.capi.check(lib.sparsh_pattern_encode(M.nrow, M.ncol, M.nnz, sp.capi.ip(M.rowptr), sp.capi.ip(M.colindex), sp.capi.dp(M.val),
+                                            dptr, pat.ctypes.data_as(C.c_void_p), sp.capi.dp(ev), sp.capi.ip(eo), sp.capi.ip(st),
+                                            C.byref(npat), C.byref(nesc)))
+    return npat.value, int(st[npat.value]), nesc.value, float(np.mean(pat[: M.nrow] == 0))
+
+
+def test_device_pattern_encoder_matches_the_host_encoder(sp, oracle, fixture_system):
+    """the upload encodes csr-pattern8 on the DEVICE (hash table + entry-by-entry verification); its table and its escape
+    rows must be the host encoder's: Poisson hierarchy levels, a level whose smoothing diagonal differs on a few rows
+    (those rows become escapes), and a matrix whose rows do not repeat (the bundled FE system: no twin)"""
+    A = oracle.gen_poisson3d(24, 20, 18)
+    H = OracleAmg(A, coarsening=0, limit_upper=300, limit_lower=150).hierarchy()
+    cases = [(L["A"], L["diag"]) for L in H.levels]
+    d2 = H.levels[0]["diag"].copy()
+    d2[[3, 77, 4001]] *= 1.0 + 1e-9
+    cases.append((A, d2))
+    checked = 0
+    for M, diag in cases:
+        dA = sp.DeviceMatrix.from_csr(M, diag=diag)
+        npat, nent, nesc, cover0 = dA.pattern_stats()
+        want = _host_pattern_encode(sp, M, diag)
+        if dA.kernel()[0] == sp.capi.KIND_PATTERN:
+            assert (npat, nent, nesc) == want[:3] and abs(cover0 - want[3]) < 1e-12
+            checked += 1
+    assert checked >= 3
+    F, _ = fixture_system
+    assert sp.DeviceMatrix.from_csr(F).pattern_stats()[0] == 0 and sp.DeviceMatrix.from_csr(F).kernel()[0] == sp.capi.KIND_STREAM
+
+
 @pytest.mark.parametrize("coarsening", [0, 1])
 @pytest.mark.parametrize("threads", [128, 256])
-def test_dict_format_is_bit_identical(sp, oracle, coarsening, threads):
+def test_dict_format_is_bit_identical(sp, oracle, coarsening, threads, monkeypatch):
     """csr-dict16 (2 B/nnz) against the oracle AND against the plain stream kernel on every level of a Poisson
     hierarchy: lossless re-encoding, same summation order -> identical bits."""
+    monkeypatch.setenv("SPARSH_DICT", "2")  # build the csr-dict16 twin even where csr-pattern8 is selected
     A = oracle.gen_poisson3d(24, 20, 18)
     H = OracleAmg(A, coarsening=coarsening, limit_upper=300, limit_lower=150).hierarchy()
     rng = np.random.default_rng(17)
