@@ -95,6 +95,9 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
 __device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(u64 *p, u64 v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ long long wall_ns() {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -155,8 +158,8 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(ticket, 1u);
         if (t == gridDim.x - 1) {
-            __threadfence_system();
-            for (int q = 0; q < a.nnbr; q++) st_release_sys(a.flag_dst[q], prev + 1);
+            __threadfence_system();  // one fence, then the flags back to back (relaxed stores behind a fence: release)
+            for (int q = 0; q < a.nnbr; q++) st_relaxed_sys(a.flag_dst[q], prev + 1);
             *reinterpret_cast<volatile u64 *>(seq) = prev + 1;
             *ticket = 0u;
             __threadfence();

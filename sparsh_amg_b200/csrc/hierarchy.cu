@@ -10,7 +10,10 @@
 // prolongation-correction; the first sweep after "X = 0" needs no matrix pass at all (A*0 = 0 exactly).
 // The whole cycle is captured into a CUDA graph: a 14-level hierarchy is ~250 launches, most of them on levels too
 // small to hide launch latency otherwise.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "hierarchy.cuh"
@@ -148,10 +151,15 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
                 rc = sparsh_matrix_create_transpose(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, &L.R);
         }
     }
+    static const bool timing = getenv("SPARSH_UPLOAD_TIMING") != nullptr;
+    const auto t_levels = std::chrono::steady_clock::now();
     if (rc == SPARSH_OK) {
         const sparsh_level_desc &d = levels[nlevels - 1];
         rc = coarse_build_inverse(d.nrow, d.rowptr, d.colindex, d.val, &h->coarse);
     }
+    if (timing)
+        std::fprintf(stderr, "[upload] coarse inverse (n = %d): %.3f s\n", levels[nlevels - 1].nrow,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_levels).count());
     if (rc == SPARSH_OK && cudaMalloc(&h->d_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
     if (rc == SPARSH_OK && cudaMallocHost(&h->h_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
     if (rc != SPARSH_OK) {

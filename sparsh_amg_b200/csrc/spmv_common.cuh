@@ -54,6 +54,11 @@ __device__ __forceinline__ sparsh_u64 ld_acquire_sys_u64(const sparsh_u64 *p) {
 __device__ __forceinline__ void st_release_sys_u64(sparsh_u64 *p, sparsh_u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// a flag store that follows a __threadfence_system() of the same thread: the fence orders everything before it, so
+// several flags can go out back to back without paying one system-scope membar each (st.release = membar + store)
+__device__ __forceinline__ void st_relaxed_sys_u64(sparsh_u64 *p, sparsh_u64 v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 struct HaloTurn {
     sparsh_u64 want, prev;
 };
@@ -101,13 +106,15 @@ __device__ __forceinline__ void halo_done(const HaloSync &hs, const HaloTurn &t)
     if (threadIdx.x == 0) {
         const unsigned int k = atomicAdd(hs.ticket, 1u);
         if (k == (unsigned int)hs.nstrip - 1u) {  // the last STRIP CTA: neighbours hear from us while the interior still runs
+            // every strip CTA fenced (system scope) before it took its ticket; ONE more fence here orders all of that
+            // before the acks and flags, which then leave back to back as relaxed stores
+            __threadfence_system();
             if (hs.nnbr > 0) {
                 *reinterpret_cast<volatile sparsh_u64 *>(hs.expect) = t.want;
-                for (int q = 0; q < hs.nnbr; q++) st_release_sys_u64(hs.ack_dst[q], t.want);
+                for (int q = 0; q < hs.nnbr; q++) st_relaxed_sys_u64(hs.ack_dst[q], t.want);
             }
             if (hs.nsend > 0) {
-                __threadfence_system();
-                for (int q = 0; q < hs.nsend; q++) st_release_sys_u64(hs.flag_dst[q], t.prev + 1);
+                for (int q = 0; q < hs.nsend; q++) st_relaxed_sys_u64(hs.flag_dst[q], t.prev + 1);
                 *reinterpret_cast<volatile sparsh_u64 *>(hs.seq) = t.prev + 1;
             }
             *hs.ticket = 0u;
