@@ -10,10 +10,15 @@
 // prolongation-correction; the first sweep after "X = 0" needs no matrix pass at all (A*0 = 0 exactly).
 // The whole cycle is captured into a CUDA graph: a 14-level hierarchy is ~250 launches, most of them on levels too
 // small to hide launch latency otherwise.
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <utility>
 
 #include "hierarchy.cuh"
@@ -119,18 +124,12 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
         sparsh_params_default(&h->prm);
     h->lev.resize(nlevels);
     int rc = SPARSH_OK;
+    // ---- validation first (sequential), then the uploads as independent tasks
     for (int l = 0; l < nlevels && rc == SPARSH_OK; l++) {
         const sparsh_level_desc &d = levels[l];
         Level &L = h->lev[l];
         L.n = d.nrow;
-        rc = sparsh_matrix_create(d.nrow, d.nrow, d.nnz, d.rowptr, d.colindex, d.val, d.diag, &L.A);
-        if (rc != SPARSH_OK) break;
-        const size_t bytes = sizeof(double) * ((size_t)d.nrow + 2);
-        if (cudaMalloc(&L.tbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
-        if (l > 0 && rc == SPARSH_OK) {
-            if (cudaMalloc(&L.xbuf, bytes) != cudaSuccess || cudaMalloc(&L.bbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
-        }
-        if (h->prm.smoother == 1 && l < nlevels - 1 && rc == SPARSH_OK) {
+        if (h->prm.smoother == 1 && l < nlevels - 1) {
             if (!d.color_count || d.total_colors < 1 || d.color_count[0] != 0 || d.color_count[d.total_colors] != d.nrow) {
                 set_error("multicolour smoother: level lacks a valid colour table");
                 rc = SPARSH_ERR_INVALID;
@@ -138,28 +137,95 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
             }
             L.color_count.assign(d.color_count, d.color_count + d.total_colors + 1);
         }
-        if (l < nlevels - 1 && rc == SPARSH_OK) {
-            if (d.p_rowptr == nullptr || d.p_ncol != levels[l + 1].nrow) {
-                set_error("prolongator missing or its column count differs from the next level's row count");
-                rc = SPARSH_ERR_INVALID;
-                break;
-            }
-            if (cudaMalloc(&L.rbuf, bytes) != cudaSuccess) rc = SPARSH_ERR_CUDA;
-            if (rc == SPARSH_OK)
-                rc = sparsh_matrix_create(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, nullptr, &L.P);
-            if (rc == SPARSH_OK)
-                rc = sparsh_matrix_create_transpose(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, &L.R);
+        if (l < nlevels - 1 && (d.p_rowptr == nullptr || d.p_ncol != levels[l + 1].nrow)) {
+            set_error("prolongator missing or its column count differs from the next level's row count");
+            rc = SPARSH_ERR_INVALID;
         }
     }
-    static const bool timing = getenv("SPARSH_UPLOAD_TIMING") != nullptr;
-    const auto t_levels = std::chrono::steady_clock::now();
-    if (rc == SPARSH_OK) {
-        const sparsh_level_desc &d = levels[nlevels - 1];
-        rc = coarse_build_inverse(d.nrow, d.rowptr, d.colindex, d.val, &h->coarse);
+    // One task per operator (A_l, P_l, R_l = P_l^T incl. its host transpose), the work vectors of a level, and the
+    // coarse inverse: independent, so they are spread over a few host threads, each copying on a stream of its own —
+    // pageable host arrays go through the driver's staging buffers one cudaMemcpy at a time per thread, and the O(nnz)
+    // host passes (validation, row statistics, transposes) overlap with the copies of the other threads.
+    // SPARSH_UPLOAD_THREADS=1 restores the sequential upload.
+    struct Task {
+        int level, what;  // 0 A, 1 P, 2 R, 3 vectors, 4 coarse inverse
+        long long weight;
+    };
+    std::vector<Task> tasks;
+    for (int l = 0; l < nlevels; l++) {
+        tasks.push_back(Task{l, 0, (long long)levels[l].nnz * 3});
+        tasks.push_back(Task{l, 3, (long long)levels[l].nrow / 8});
+        if (l < nlevels - 1) {
+            tasks.push_back(Task{l, 1, (long long)levels[l].p_nnz * 2});
+            tasks.push_back(Task{l, 2, (long long)levels[l].p_nnz * 4});
+        }
     }
-    if (timing)
-        std::fprintf(stderr, "[upload] coarse inverse (n = %d): %.3f s\n", levels[nlevels - 1].nrow,
-                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_levels).count());
+    tasks.push_back(Task{nlevels - 1, 4, (long long)levels[nlevels - 1].nrow * levels[nlevels - 1].nrow * 50});
+    std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.weight > b.weight; });
+    static const bool timing = getenv("SPARSH_UPLOAD_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto run_task = [&](const Task &t) -> int {
+        const sparsh_level_desc &d = levels[t.level];
+        Level &L = h->lev[t.level];
+        const size_t bytes = sizeof(double) * ((size_t)d.nrow + 2);
+        switch (t.what) {
+            case 0:
+                return sparsh_matrix_create(d.nrow, d.nrow, d.nnz, d.rowptr, d.colindex, d.val, d.diag, &L.A);
+            case 1:
+                return sparsh_matrix_create(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, nullptr, &L.P);
+            case 2:
+                return sparsh_matrix_create_transpose(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, &L.R);
+            case 3:
+                SP_CUDA(cudaMalloc(&L.tbuf, bytes));
+                if (t.level > 0) {
+                    SP_CUDA(cudaMalloc(&L.xbuf, bytes));
+                    SP_CUDA(cudaMalloc(&L.bbuf, bytes));
+                }
+                if (t.level < nlevels - 1) SP_CUDA(cudaMalloc(&L.rbuf, bytes));
+                return SPARSH_OK;
+            default:
+                return coarse_build_inverse(d.nrow, d.rowptr, d.colindex, d.val, &h->coarse);
+        }
+    };
+    if (rc == SPARSH_OK) {
+        int nthreads = (int)std::min<size_t>({tasks.size(), (size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)8});
+        if (const char *e = getenv("SPARSH_UPLOAD_THREADS")) nthreads = std::max(1, std::min(atoi(e), 64));
+        std::atomic<size_t> next{0};
+        std::atomic<int> first_rc{SPARSH_OK};
+        std::mutex err_mutex;
+        std::string err_msg;
+        const int device = ctx().device;
+        auto worker = [&](bool own_stream) {
+            cudaStream_t s = nullptr;
+            if (own_stream) {
+                cudaSetDevice(device);  // the runtime's current device is per host thread
+                if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) set_upload_stream(s);
+            }
+            for (size_t i = next++; i < tasks.size(); i = next++) {
+                if (first_rc.load() != SPARSH_OK) break;
+                const int trc = run_task(tasks[i]);
+                if (trc != SPARSH_OK) {
+                    std::lock_guard<std::mutex> g(err_mutex);
+                    int expect = SPARSH_OK;
+                    if (first_rc.compare_exchange_strong(expect, trc)) err_msg = sparsh_last_error();  // this thread's message
+                }
+            }
+            if (s) {
+                cudaStreamSynchronize(s);
+                set_upload_stream(nullptr);
+                cudaStreamDestroy(s);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, true);
+        worker(nthreads > 1);  // the calling thread works too (on a stream of its own when it has company)
+        for (auto &th : pool) th.join();
+        rc = first_rc.load();
+        if (rc != SPARSH_OK) set_error(err_msg);
+        if (timing)
+            std::fprintf(stderr, "[upload] %zu tasks on %d host threads: %.3f s\n", tasks.size(), nthreads,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    }
     if (rc == SPARSH_OK && cudaMalloc(&h->d_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
     if (rc == SPARSH_OK && cudaMallocHost(&h->h_sc, sizeof(double) * 16) != cudaSuccess) rc = SPARSH_ERR_CUDA;
     if (rc != SPARSH_OK) {

@@ -266,6 +266,10 @@ int k_maxpy_sub(size_t n, const double *V, size_t ld, int k, const double *d_h, 
 int k_lincomb(size_t n, const double *V, size_t ld, int k, const double *d_y, double *out);
 int k_scale_inv_sqrt(size_t n, const double *in, const double *d_nrm2, double *out);
 
+// matrix uploads issued by the calling host thread go to `s` (nullptr: the library's stream) — hierarchy.cu builds the
+// levels of a hierarchy with several host threads, each on a stream of its own
+void set_upload_stream(cudaStream_t s);
+
 // ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------
 struct CoarseInverse {
     int n = 0;

@@ -48,8 +48,16 @@ void choose_kernel(sparsh_matrix_s *A, const int *rp) {
     }
 }
 
+// uploads run on the library's stream, or on the calling thread's own stream while sparsh_hierarchy_create builds the
+// levels with several host threads (set_upload_stream)
+thread_local cudaStream_t t_upload_stream = nullptr;
+struct UpStream {
+    cudaStream_t stream;
+};
+UpStream up() { return UpStream{t_upload_stream ? t_upload_stream : ctx().stream}; }
+
 int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, const double *diag) {
-    Context &c = ctx();
+    const UpStream c = up();
     const int n = A->nrow, nnz = A->nnz;
     // padding: the stream kernel's bulk copies round the slice [rowptr[r0], rowptr[r1]) outwards to multiples of 4
     const size_t pad_nnz = (((size_t)nnz + 3) & ~(size_t)3) + 8;
@@ -182,7 +190,7 @@ bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *
     std::vector<unsigned short> code(nnz);
     if (!dict_encode(n, rp, ci, v, code.data(), dv, dof)) return false;
     const size_t pad = ((nnz + 7) & ~(size_t)7) + 16;  // bulk copies round the slice outwards to multiples of 8 codes
-    cudaStream_t st = ctx().stream;
+    cudaStream_t st = up().stream;
     if (cudaMalloc(&A->code, sizeof(unsigned short) * pad) != cudaSuccess) return false;
     cudaMalloc(&A->dict_val, sizeof(double) * 256);
     cudaMalloc(&A->dict_off, sizeof(int) * 256);
@@ -435,7 +443,7 @@ int pattern_mode() {
 bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, const double *h_diag) {
     const int n = A->nrow;
     if (n == 0 || A->nnz == 0) return false;
-    cudaStream_t st = ctx().stream;
+    cudaStream_t st = up().stream;
     PatSlot *d_table = nullptr;
     int *d_slot_of = nullptr, *d_overflow = nullptr, *d_id_of = nullptr;
     unsigned long long *d_counts = nullptr;
@@ -592,6 +600,10 @@ int validate(int nrow, int ncol, int nnz, const int *rp, const int *ci) {
 }
 
 }  // namespace
+
+namespace sparsh {
+void set_upload_stream(cudaStream_t s) { t_upload_stream = s; }
+}  // namespace sparsh
 
 extern "C" {
 
