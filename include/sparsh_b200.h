@@ -114,6 +114,20 @@ int sparsh_matrix_pattern_stats(sparsh_matrix_t A, int *n_pat, int *n_ent, int *
 int sparsh_pattern_windows(int n_ent, const int *ent_off, int *tile, int *nwin, int *lo, int *len, int *w0,
                            unsigned char *win);
 
+/* ------------------------------------------------------------------ setup ------ */
+/* Galerkin product A_c = P^T (A P) on the device: what parallel::coarsen_matrix does with two
+ * mkl_sparse_spmm calls on the host (src/AMG_cycle_utilities.cpp:126-146).  Row-wise products with the host setup's
+ * traversal order and unfused arithmetic, columns sorted: row pointers and column indices equal the reference's, values
+ * equal this repository's host product bit for bit.  On return *out holds the product on the device and *nnz_coarse its
+ * entry count; *out == NULL with SPARSH_OK means "not applicable" (a product row longer than the kernel's per-thread
+ * list: use the host product).  sparsh_rap_fetch copies it into caller arrays (rowptr[ncoarse+1], colindex, val). */
+typedef struct sparsh_rap_s *sparsh_rap_t;
+int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, const double *h_val, int ncoarse,
+                        const int *h_p_rowptr, const int *h_p_colindex, const double *h_p_val, sparsh_rap_t *out,
+                        int *nnz_coarse);
+int sparsh_rap_fetch(sparsh_rap_t h, int *h_rowptr, int *h_colindex, double *h_val);
+int sparsh_rap_destroy(sparsh_rap_t h);
+
 /* ------------------------------------------------------------------ per-op ----- */
 /* K9  y = A x                              cusparseDcsrmv, e.g. src/AMG_main_solvers.cu:100,221,354 */
 int sparsh_spmv(sparsh_matrix_t A, const double *d_x, double *d_y);

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const double *__restric
 
 int coarse_build_inverse(int n, const int *rp, const int *ci, const double *v, CoarseInverse *out) {
     Context &c = ctx();
+    NvtxRange nvtx("sparsh:coarse-inverse");
     if (n > 16384) {
         set_error("coarsest level too large for the dense device solve (n > 16384): coarsen further (raise level1)");
         return SPARSH_ERR_INVALID;

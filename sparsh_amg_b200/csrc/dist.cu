@@ -866,6 +866,7 @@ static int build_dist_hierarchy(sparsh_dist_s *h, int nd, const sparsh_dist_leve
                                 const sparsh_params *params) {
     Comm &m = comm();
     SP_REQUIRE(m.comm != nullptr || m.nranks == 1, "sparsh_dist_init has not been called");
+    NvtxRange nvtx("sparsh:dist-upload");
     SP_TRY(ensure_aux_stream(m));  // single-rank use without NCCL (tests) still needs the stream/event plumbing
     if (params)
         h->prm = *params;
@@ -1157,6 +1158,7 @@ int sparsh_dist_vcycle(sparsh_dist_t h, const double *d_b_local, double *d_x_loc
 // reductions of an iteration are completed by in-place all-reduces of device scalars.
 int sparsh_dist_pcg(sparsh_dist_t h, const double *b, double *x, double tol, int max_iter, double *hist, int *iters_out) {
     SP_TRY(check_alive(h));
+    NvtxRange nvtx("sparsh:dist-pcg");
     Context &c = ctx();
     DistLevel &L0 = h->lev[0];
     const size_t n = (size_t)L0.n;

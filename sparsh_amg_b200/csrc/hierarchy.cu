@@ -117,6 +117,7 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
                             sparsh_hierarchy_t *out) {
     SP_TRY(ensure_init());
     SP_REQUIRE(nlevels >= 1 && levels != nullptr && out != nullptr, "bad hierarchy description");
+    NvtxRange nvtx("sparsh:upload");
     sparsh_hierarchy_s *h = new sparsh_hierarchy_s();
     if (params)
         h->prm = *params;
@@ -215,6 +216,7 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
                 set_upload_stream(nullptr);
                 cudaStreamDestroy(s);
             }
+            if (own_stream) release_upload_stage();
         };
         std::vector<std::thread> pool;
         for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, true);
@@ -293,6 +295,7 @@ int sparsh_hierarchy_amg_solve(sparsh_hierarchy_t h, const double *d_b, double *
     SP_REQUIRE(h != nullptr, "hierarchy is NULL");
     sparsh_matrix_s *A = h->lev[0].A;
     double r1 = 0.0;
+    NvtxRange nvtx("sparsh:amg-solve");
     SP_TRY(sparsh_residual_norm(A, d_b, d_x, &r1));  // reference src/AMG_phases.cpp:159
     if (h_hist) h_hist[0] = r1;
     int cycles = 0;

@@ -70,6 +70,7 @@ int run_graphed(sparsh_hierarchy_s *h, const void *k0, const void *k1, int tag, 
         return body();
     }
     if (!ent->exec) {
+        NvtxRange nvtx("sparsh:graph-capture");
         cudaGraph_t graph = nullptr;
         SP_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
         c.capturing = true;

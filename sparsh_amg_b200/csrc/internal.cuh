@@ -6,6 +6,8 @@
 
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (dlopen's the tools library when a profiler is attached; a no-op otherwise)
+
 #include "../../include/sparsh_b200.h"
 
 namespace sparsh {
@@ -31,6 +33,15 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
             return SPARSH_ERR_INVALID;    \
         }                                 \
     } while (0)
+
+// ---- NVTX ranges (the reference links nvToolsExt without using it, CMakeLists.txt:42): phases of the solve show up by
+// name in ncu / nsys timelines: sparsh:upload, sparsh:coarse-inverse, sparsh:pcg, sparsh:bicgstab, sparsh:amg-solve, ...
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // ---- runtime context --------------------------------------------------------------------------------
 struct Context {
@@ -269,6 +280,7 @@ int k_scale_inv_sqrt(size_t n, const double *in, const double *d_nrm2, double *o
 // matrix uploads issued by the calling host thread go to `s` (nullptr: the library's stream) — hierarchy.cu builds the
 // levels of a hierarchy with several host threads, each on a stream of its own
 void set_upload_stream(cudaStream_t s);
+void release_upload_stage();  // frees the calling thread's pinned staging buffers (matrix.cu)
 
 // ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------
 struct CoarseInverse {

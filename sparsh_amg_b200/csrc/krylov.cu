@@ -68,6 +68,7 @@ struct TmpHier {
 // precond = false: Solver_CG_1,  src/AMG_main_solvers.cpp:47-103 (r = b: assumes x0 = 0, kept as in the reference)
 int cg_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, double tol, int max_iter, double *hist,
             int *iters_out) {
+    NvtxRange nvtx(precond ? "sparsh:pcg" : "sparsh:cg");
     sparsh_matrix_s *A = h->lev[0].A;
     const size_t n = (size_t)A->nrow;
     SP_TRY(krylov_workspace(h, 4));
@@ -141,6 +142,7 @@ int cg_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, dou
 // precond = false: Solver_BiCG_1,  src/AMG_main_solvers.cpp:271-355
 int bicg_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, double tol, int max_iter, double *hist,
               int *iters_out) {
+    NvtxRange nvtx(precond ? "sparsh:pbicgstab" : "sparsh:bicgstab");
     sparsh_matrix_s *A = h->lev[0].A;
     const size_t n = (size_t)A->nrow;
     SP_TRY(krylov_workspace(h, 8));
@@ -198,6 +200,7 @@ int bicg_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, d
 // CUDA graph as PCG's (the basis vector is staged through a fixed input vector).
 int gmres_impl(sparsh_hierarchy_s *h, bool precond, const double *b, double *x, double tol, int restart, int max_iter,
                double *hist, int *iters_out) {
+    NvtxRange nvtx(precond ? "sparsh:pgmres" : "sparsh:gmres");
     sparsh_matrix_s *A = h->lev[0].A;
     const size_t n = (size_t)A->nrow;
     const size_t ld = (n + 3) & ~(size_t)3;  // basis vectors 32-byte aligned

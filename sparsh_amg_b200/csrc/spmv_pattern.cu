@@ -6,7 +6,7 @@
 //    in the kernel parameters (Pat0, internal.cuh), so its offsets are constant-bank operands known before anything is
 //    loaded: every thread issues the pattern byte, b, x_i AND all gathers of pattern 0 for all its rows at once —
 //    one round trip — and only looks at the pattern byte when the data is there.  Rows that turn out to carry another
-//    pattern (boundary rows, a few per cent) are redone from the shared-memory table, escapes from the CSR arrays;
+//    pattern (boundary rows, a few per cent) are redone from the table in global memory, escapes from the CSR arrays;
 //  * ~250 instructions per row of predicated 8-wide steps, selects and shared-memory look-ups (ncu on the dict kernel:
 //    issue slots 65 % busy, ALU the top pipe).  The fast path is straight-line code: per entry one integer add, one
 //    address computation, one LDG, one DMUL and one DADD whose second operands come from the constant bank;
@@ -157,12 +157,13 @@ int launch_cfg(const sparsh_matrix_s *A, const double *x, double *y, const EpiAr
         return SPARSH_ERR_INVALID;
     }
     const PatView P = A->pattern(args.d != nullptr && args.d == A->diag);
-    // prefetch distance = CTAs of this kernel that are resident at a time (SPARSH_PAT2_PF overrides; 0 switches it off)
+    // successor-tile L2 prefetch: OFF by default.  Measured (profiles/r02g_pattern_lean_v3_sweep.log, ncu source page in
+    // profiles/r02m_*): it buys 1.5 % of the sweep while its index arithmetic is 28 of the 182 instructions a warp
+    // executes in a kernel that ncu shows issue-bound (76 % issue-active, DRAM 41 %).  SPARSH_PAT2_PF=<tiles> enables it
+    // (a sensible distance is the number of co-resident CTAs, sm_count x 8).
     static const int pf = [] {
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false>, THREADS, 0);
         const char *e = getenv("SPARSH_PAT2_PF");
-        return e ? atoi(e) : ctx().sm_count * std::max(per_sm, 1);
+        return e ? atoi(e) : 0;
     }();
     if (d.dist)
         csr_pat2_kernel<THREADS, RPT, LEN0, EPI, true><<<grid, THREADS, 0, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf);

@@ -190,6 +190,26 @@ class DeviceMatrix:
             pass
 
 
+def galerkin_rap(A, P):
+    """A_c = P^T (A P) computed on the device (sparsh_galerkin_rap) -> (rowptr, colindex, val) numpy arrays, or None when
+    the device kernel does not apply (a product row longer than its per-thread list)"""
+    lib = capi.load()
+    h, nnz = C.c_void_p(), C.c_int()
+    rp, ci, v = (np.ascontiguousarray(A.rowptr, dtype=np.int32), np.ascontiguousarray(A.colindex, dtype=np.int32),
+                 np.ascontiguousarray(A.val, dtype=np.float64))
+    prp, pci, pv = (np.ascontiguousarray(P.rowptr, dtype=np.int32), np.ascontiguousarray(P.colindex, dtype=np.int32),
+                    np.ascontiguousarray(P.val, dtype=np.float64))
+    check(lib.sparsh_galerkin_rap(A.nrow, ip(rp), ip(ci), dp(v), P.ncol, ip(prp), ip(pci), dp(pv), C.byref(h), C.byref(nnz)))
+    if not h.value:
+        return None
+    out_rp = np.zeros(P.ncol + 1, dtype=np.int32)
+    out_ci = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    out_v = np.zeros(max(nnz.value, 1))
+    check(lib.sparsh_rap_fetch(h, ip(out_rp), ip(out_ci), dp(out_v)))
+    check(lib.sparsh_rap_destroy(h))
+    return out_rp, out_ci[: nnz.value], out_v[: nnz.value]
+
+
 def _krylov(fn, handle, b, x, tol, max_iter):
     hist = np.zeros(max_iter + 1)
     it = C.c_int()

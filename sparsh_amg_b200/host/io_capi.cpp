@@ -323,6 +323,7 @@ int sparsh_host_set_option(const char *name, double value) {
     else if (s == "use_graph") o.use_graph = (int)value;
     else if (s == "halo_mode") o.halo_mode = (int)value;
     else if (s == "device") o.device = (int)value;
+    else if (s == "gpu_rap") o.gpu_rap = (int)value;
     else if (s == "tail_threshold") o.tail_threshold = (int)value;
     else if (s == "gmres_restart") o.gmres_restart = (int)value;
     else if (s == "sa_theta") o.sa_theta = value;

@@ -16,9 +16,11 @@
 #include <iostream>
 #include <memory>
 #include <numeric>
+#include <cstdio>
 #include <type_traits>
 #include <vector>
 
+#include "../../include/sparsh_b200.h"
 #include "sparsh_amg.hpp"
 
 namespace sparsh {
@@ -574,6 +576,31 @@ void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
     Csr AP, R, C;
     const bool tm = getenv("SPARSH_SETUP_TIMING") != nullptr;
     double t0 = omp_get_wtime();
+    if (options().gpu_rap) {  // same product, computed by the device (csrc/rap.cu): identical integers and values
+        sparsh_rap_t rap = nullptr;
+        int cnnz = -1;
+        const int rc = sparsh_galerkin_rap(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, &rap, &cnnz);
+        if (rc != SPARSH_OK) {
+            std::fprintf(stderr, "sparsh_amg: device Galerkin product failed (%d): %s\n", rc, sparsh_last_error());
+            std::exit(1);
+        }
+        if (rap) {
+            Ac = new sp_matrix_mg();
+            Ac->nrow = Ac->ncol = P1.ncol;
+            Ac->nnz = cnnz;
+            Ac->rowptr = new int[(size_t)P1.ncol + 1];
+            Ac->colindex = new int[(size_t)std::max(cnnz, 1)];
+            Ac->val = new double[(size_t)std::max(cnnz, 1)];
+            if (sparsh_rap_fetch(rap, Ac->rowptr, Ac->colindex, Ac->val) != SPARSH_OK) {
+                std::fprintf(stderr, "sparsh_amg: device Galerkin product: fetch failed: %s\n", sparsh_last_error());
+                std::exit(1);
+            }
+            sparsh_rap_destroy(rap);
+            Ac->sp_matrix_fill_diagonal();
+            if (tm) std::cout << "  RAP on the device: " << omp_get_wtime() - t0 << std::endl;
+            return;
+        }  // else: a product row is too long for the device kernel — the host product below
+    }
     spgemm(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, AP);
     double t1 = omp_get_wtime();
     transpose(P1.nrow, P1.ncol, P1.rowptr, P1.colindex, P1.val, R);

@@ -84,6 +84,7 @@ struct Options {
     int max_iter = 10000;          // iteration cap (the reference's AMG and BiCGStab loops have none)
     int use_graph = 1;             // CUDA-graph the V-cycle / Krylov iteration
     int halo_mode = 1;             // multi-GPU halo exchange: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv
+    int gpu_rap = 0;               // 1: Galerkin products of the setup run on the device (sparsh_galerkin_rap; same result)
     int device = -1;               // multi-GPU entry points: CUDA device of this rank (-1: the rank itself)
     int tail_threshold = 1100000;  // multi-GPU: levels with at most this many rows are replicated on every GPU
     int gmres_restart = 30;        // Solver_GMRES_1 / Solver_PGMRES_1 (used by sparsh_gmres; the host-buffer path uses 30)

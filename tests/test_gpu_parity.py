@@ -341,6 +341,48 @@ def test_gmres_matches_the_oracle_statement(sp, oracle, fixture_system):
     assert np.linalg.norm(fb - F.to_scipy() @ dfx.download()) <= 1e-8 * (1 + 1e-6)
 
 
+def test_device_galerkin_product(sp, oracle, fixture_system):
+    """A_c = P^T (A P) on the device (csrc/rap.cu) against the oracle's restatement of
+    parallel::coarsen_matrix (src/AMG_cycle_utilities.cpp:126-146) — row pointers and sorted column indices bit-exact,
+    values to 1e-13 — and against this repository's host product, whose bits it must reproduce (same traversal order,
+    unfused arithmetic): aggregation P (HEM), classical P (Beck) on 3D Poisson and on the bundled FE system, and a whole
+    hierarchy built with options().gpu_rap = 1."""
+    from sparsh_amg_b200 import host
+
+    F, _ = fixture_system
+    cases = []
+    for A in (oracle.gen_poisson3d(20, 18, 16), F):
+        nc, agg = oracle.hem(A, 0)
+        cases.append((A, CSR(A.nrow, nc, np.arange(A.nrow + 1, dtype=np.int32), agg, np.ones(A.nrow))))
+        cases.append((A, oracle.beck(A)))
+    for A, P in cases:
+        got = sp.galerkin_rap(A, P)
+        assert got is not None
+        want = oracle.rap(A, P)
+        np.testing.assert_array_equal(got[0], want.rowptr)
+        np.testing.assert_array_equal(got[1], want.colindex)
+        np.testing.assert_allclose(got[2], want.val, rtol=1e-13, atol=1e-13 * np.abs(want.val).max())
+    # a whole hierarchy, host product against device product: identical bits on every level
+    host.set_options(threads=4, max_levels=32, print_setup=0, coarse_upper=300, coarse_lower=100)
+    try:
+        for coarsening in (0, 1, 2):
+            host.set_options(coarsening=coarsening, gpu_rap=0)
+            M = host.HostMatrix.poisson3d(24, 20, 18)
+            h0 = host.HostAmg(M)
+            host.set_options(gpu_rap=1)
+            h1 = host.HostAmg(M)
+            assert h0.nlevels == h1.nlevels and h0.nlevels >= 3
+            for L0, L1 in zip(h0.levels(), h1.levels()):
+                for key in ("rowptr", "colindex", "val"):
+                    np.testing.assert_array_equal(getattr(L0["A"], key), getattr(L1["A"], key))
+                np.testing.assert_array_equal(L0["diag"], L1["diag"])
+            h0.free()
+            h1.free()
+            M.free()
+    finally:
+        host.set_options(coarsening=0, gpu_rap=0, coarse_upper=4000, coarse_lower=2000, max_levels=6, print_setup=1)
+
+
 def test_edge_cases(sp, oracle):
     # 1x1
     A = CSR(1, 1, [0, 1], [0], [2.0])
