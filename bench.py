@@ -190,7 +190,7 @@ def run_ours(args):
     grid = args.grid
     threads = os.cpu_count() or 1
     host.set_options(threads=threads, max_levels=32, print_setup=0, print_solve=0, coarsening=0, sweeps=7,
-                     use_graph=1)
+                     use_graph=1, gpu_rap=int(args.gpu_rap))
     t0 = time.time()
     A = host.HostMatrix.poisson3d(grid, grid, grid)
     t_gen = time.time() - t0
@@ -312,6 +312,7 @@ def run_ours(args):
                         "solve_effective_gbs": iter_bytes * it / solve_s / 1e9,
                         "l2": "inputs larger than L2 (finest matrix 1.4 GB vs 126 MB): no flush needed", "cuda_graph": True,
                         "host_setup_seconds": rep["setup_seconds"], "upload_seconds": rep2["upload_seconds"],
+                        "galerkin_products": "device (csrc/rap.cu)" if args.gpu_rap else "host (host/setup.cpp)",
                         "matrix_generation_seconds": t_gen},
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8,
                     "pcg_iterations": it_h},
@@ -336,6 +337,8 @@ def main():
     ap.add_argument("--share-hierarchy", action="store_true",
                     help="N>1: rank 0 builds the host hierarchy once, the other ranks map it (needed beyond 256^3)")
     ap.add_argument("--halo-mode", type=int, default=1, help="N>1: 1 NVLink peer-memory pushes, 0 ncclSend/ncclRecv")
+    ap.add_argument("--gpu-rap", action="store_true",
+                    help="N=1: the Galerkin products of the (untimed) host setup run on the device (same hierarchy, bit for bit)")
     ap.add_argument("--dump-hist", default=None, help="N=1: write the PCG residual history of the solve to this JSON file")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: honour --warmup/--max-iter literally, do not insist on convergence")

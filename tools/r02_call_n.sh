@@ -11,4 +11,4 @@ SPARSH_UPLOAD_TIMING=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu
 SPARSH_SETUP_TIMING=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --gpu-rap > "$out/bench_n1_gpurap.json" 2> "$out/bench_n1_gpurap.err"; show "N=1 device RAP" < "$out/bench_n1_gpurap.json"
 SPARSH_PAT2_RPT=2 timeout 300 python tools/perf_probe.py --n 256 --reps 20 --families pattern 2>&1 | grep -E "^pattern" | sed "s/^/rpt=2 /" | tee "$out/sweep.log"
 SPARSH_PAT2_RPT=1 timeout 300 python tools/perf_probe.py --n 256 --reps 20 --families pattern 2>&1 | grep -E "^pattern" | sed "s/^/rpt=1 /" | tee -a "$out/sweep.log"
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > "$out/sanitizer_memcheck.log" 2>&1; echo "memcheck exit $?"; tail -4 "$out/sanitizer_memcheck.log"
+echo "compute-sanitizer is closed on this pool (gpurun answers exit 86)"
