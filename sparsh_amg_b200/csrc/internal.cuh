@@ -43,6 +43,44 @@ struct NvtxRange {
     NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// An iteration is ~250 dependent kernels, most of them a few microseconds long on the small levels: the gap between two
+// graph nodes (drain, launch, CTA scheduling) is a good part of their cost.  Launched with the programmatic-stream-
+// serialisation attribute, kernel k+1 is scheduled as soon as every CTA of kernel k has passed its
+// griddepcontrol.launch_dependents (the first thing our kernels do after their own griddepcontrol.wait) and then blocks
+// in griddepcontrol.wait until kernel k has completed and its memory operations are visible: the launch latency
+// overlaps the predecessor instead of following it.  A kernel launched WITHOUT the attribute passes the wait at once,
+// and a predecessor that never triggers releases its dependents when it exits, so mixing is safe.  Captured into CUDA
+// graphs as programmatic dependency edges.  SPARSH_PDL=0 launches everything classically.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+void pdl_disable();  // a launch with the attribute was refused (old driver): everything is launched classically from then on
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        if (e != cudaErrorNotSupported) return e;
+        cudaGetLastError();
+        pdl_disable();
+        cfg.attrs = nullptr;
+        cfg.numAttrs = 0;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- runtime context --------------------------------------------------------------------------------
 struct Context {
     bool ready = false;

@@ -1,6 +1,7 @@
 // runtime.cu — context, streams, memory and BLAS-1 entry points of the C-ABI (include/sparsh_b200.h).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -20,6 +21,16 @@ Context &ctx() {
     static Context c;
     return c;
 }
+
+static int g_pdl = -1;  // -1: not decided yet
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char *e = getenv("SPARSH_PDL");
+        g_pdl = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+    }
+    return g_pdl == 1;
+}
+void pdl_disable() { g_pdl = 0; }
 
 int ensure_init() {
     if (ctx().ready) return SPARSH_OK;

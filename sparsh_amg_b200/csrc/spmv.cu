@@ -25,6 +25,7 @@ namespace sparsh {
 // stage 2: a single CTA adds the partials in index order (65536 per-block atomics on one ticket cost ~60 us on a
 // 256^3 SpMV; this kernel costs ~4 us and keeps the result independent of block scheduling)
 __global__ void __launch_bounds__(1024) finalize_partials_kernel(const double *__restrict__ partials, int count, double *out) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     __shared__ double sred[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < count; i += 1024) acc += partials[i];
@@ -39,6 +40,7 @@ template <int THREADS, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_stream_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, int cap, double *partials,
                       HaloSync hs) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sval = reinterpret_cast<double *>(smem_raw);
     int *scol = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(double));
@@ -115,6 +117,7 @@ template <int THREADS, int RPT, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_dict_kernel(CsrView A, DictView D, const double *x, double *y, EpiArgs args, RowRange rr, int cap,
                     double *partials, HaloSync hs) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     // One CTA owns THREADS*RPT consecutive rows, thread t the rows r0 + s*THREADS + t (s < RPT).  With 2 B/nnz a
     // 256-row tile is only ~4 KB of matrix: a CTA must own several tiles' worth of rows, or the fixed cost of a CTA
     // (row pointer fetch -> bulk copy -> wait) caps the bytes in flight per SM below what saturates HBM.
@@ -217,6 +220,7 @@ template <int THREADS, int RPT, int JB, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_pattern_kernel(CsrView A, PatView P, const double *x, double *y, EpiArgs args, RowRange rr, double *partials,
                        HaloSync hs) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     constexpr bool NEEDS_D = (EPI == EPI_JACOBI || EPI == EPI_SOR);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sval = reinterpret_cast<double *>(smem_raw);   // n_ent values
@@ -329,6 +333,7 @@ template <int THREADS, int EPI>
 __global__ void __launch_bounds__(THREADS)
     csr_pattern_tma_kernel(CsrView A, PatView P, PatWindows W, const double *x, double *y, EpiArgs args, RowRange rr,
                            double *partials) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     constexpr int RPT = PAT_TILE / THREADS;
     constexpr bool NEEDS_B = (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM);
     constexpr bool NEEDS_D = (EPI == EPI_JACOBI || EPI == EPI_SOR);
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(THREADS)
 template <int THREADS, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_scalar_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     int r0, row_end;
     block_rows(rr, THREADS, r0, row_end);
     const int row = r0 + threadIdx.x;
@@ -460,6 +466,7 @@ __global__ void __launch_bounds__(THREADS)
 template <int LANES, int EPI, bool DIST>
 __global__ void __launch_bounds__(256)
     csr_vector_kernel(CsrView A, const double *x, double *y, EpiArgs args, RowRange rr, double *partials, HaloSync hs) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     constexpr int ROWS_PER_CTA = 256 / LANES;
     const int lane = threadIdx.x % LANES;
     int r0, row_end;
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------
 int launch_finalize_partials(int count, double *out) {
     Context &c = ctx();
-    finalize_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials, count, out);
+    SP_CUDA(launch_k(finalize_partials_kernel, dim3(1), dim3(1024), 0, c.stream, c.partials, count, out));
     count_launch();
     SP_CUDA(cudaGetLastError());
     return SPARSH_OK;
@@ -527,9 +534,9 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_stream_kernel<THREADS, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_stream_kernel<THREADS, EPI, true>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), x, y, args, d.rr, cap, c.partials, d.hs));
     else
-        csr_stream_kernel<THREADS, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), x, y, args, d.rr, cap, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_stream_kernel<THREADS, EPI, false>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), x, y, args, d.rr, cap, c.partials, d.hs));
     return finish_launch<EPI>(grid, args);
 }
 
@@ -565,9 +572,9 @@ static int launch_dict_rpt(const sparsh_matrix_s *A, const double *x, double *y,
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_dict_kernel<THREADS, RPT, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_dict_kernel<THREADS, RPT, EPI, true>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs));
     else
-        csr_dict_kernel<THREADS, RPT, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_dict_kernel<THREADS, RPT, EPI, false>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), A->dict(), x, y, args, d.rr, cap, c.partials, d.hs));
     return finish_launch<EPI>(grid, args);
 }
 
@@ -614,9 +621,9 @@ static int launch_pattern_cfg(const sparsh_matrix_s *A, const double *x, double 
     // a kernel may use without opting in
     const size_t smem = (size_t)A->n_pent * 12 + (size_t)A->n_pat * 8 + (size_t)(A->n_pat + 1) * 4;
     if (d.dist)
-        csr_pattern_kernel<THREADS, RPT, JB, EPI, true><<<grid, THREADS, smem, c.stream>>>(A->view(), P, x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_pattern_kernel<THREADS, RPT, JB, EPI, true>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), P, x, y, args, d.rr, c.partials, d.hs));
     else
-        csr_pattern_kernel<THREADS, RPT, JB, EPI, false><<<grid, THREADS, smem, c.stream>>>(A->view(), P, x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_pattern_kernel<THREADS, RPT, JB, EPI, false>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), P, x, y, args, d.rr, c.partials, d.hs));
     return finish_launch<EPI>(grid, args);
 }
 
@@ -646,7 +653,7 @@ static int launch_pattern_tma(const sparsh_matrix_s *A, const double *x, double 
         return SPARSH_ERR_INVALID;
     }
     const PatView P = A->pattern(args.d != nullptr && args.d == A->diag);
-    csr_pattern_tma_kernel<THREADS, EPI><<<grid, THREADS, smem, c.stream>>>(A->view(), P, W, x, y, args, d.rr, c.partials);
+    SP_CUDA(launch_k(csr_pattern_tma_kernel<THREADS, EPI>, dim3(grid), dim3(THREADS), smem, c.stream, A->view(), P, W, x, y, args, d.rr, c.partials));
     return finish_launch<EPI>(grid, args);
 }
 
@@ -683,9 +690,9 @@ static int launch_scalar(const sparsh_matrix_s *A, const double *x, double *y, c
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_scalar_kernel<256, EPI, true><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_scalar_kernel<256, EPI, true>, dim3(grid), dim3(256), 0, c.stream, A->view(), x, y, args, d.rr, c.partials, d.hs));
     else
-        csr_scalar_kernel<256, EPI, false><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_scalar_kernel<256, EPI, false>, dim3(grid), dim3(256), 0, c.stream, A->view(), x, y, args, d.rr, c.partials, d.hs));
     return finish_launch<EPI>(grid, args);
 }
 
@@ -698,9 +705,9 @@ static int launch_vector(const sparsh_matrix_s *A, const double *x, double *y, c
         return SPARSH_ERR_INVALID;
     }
     if (d.dist)
-        csr_vector_kernel<LANES, EPI, true><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_vector_kernel<LANES, EPI, true>, dim3(grid), dim3(256), 0, c.stream, A->view(), x, y, args, d.rr, c.partials, d.hs));
     else
-        csr_vector_kernel<LANES, EPI, false><<<grid, 256, 0, c.stream>>>(A->view(), x, y, args, d.rr, c.partials, d.hs);
+        SP_CUDA(launch_k(csr_vector_kernel<LANES, EPI, false>, dim3(grid), dim3(256), 0, c.stream, A->view(), x, y, args, d.rr, c.partials, d.hs));
     return finish_launch<EPI>(grid, args);
 }
 

@@ -50,6 +50,7 @@ template <int THREADS, int RPT, int LEN0, int EPI, bool DIST>
 __global__ void __launch_bounds__(THREADS)
     csr_pat2_kernel(CsrView A, PatView P, const __grid_constant__ Pat0 Z, const double *x, double *y, EpiArgs args,
                     RowRange rr, double *partials, HaloSync hs, int pf_dist) {
+    pdl_prologue();  // PDL: wait for the predecessor grid, then let the successor be scheduled
     constexpr bool NEEDS_B = (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_SOR || EPI == EPI_RESNORM);
     constexpr bool NEEDS_D = (EPI == EPI_JACOBI || EPI == EPI_SOR);
     constexpr bool COH = EpiTraits<EPI>::coherent_x;
@@ -166,9 +167,9 @@ int launch_cfg(const sparsh_matrix_s *A, const double *x, double *y, const EpiAr
         return e ? atoi(e) : 0;
     }();
     if (d.dist)
-        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, true><<<grid, THREADS, 0, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf);
+        SP_CUDA(launch_k(csr_pat2_kernel<THREADS, RPT, LEN0, EPI, true>, dim3(grid), dim3(THREADS), 0, c.stream, A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf));
     else
-        csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false><<<grid, THREADS, 0, c.stream>>>(A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf);
+        SP_CUDA(launch_k(csr_pat2_kernel<THREADS, RPT, LEN0, EPI, false>, dim3(grid), dim3(THREADS), 0, c.stream, A->view(), P, A->pat0, x, y, args, d.rr, c.partials, d.hs, pf));
     count_launch();
     SP_CUDA(cudaGetLastError());
     if (EpiTraits<EPI>::reduces) return launch_finalize_partials(grid, args.red_out);

@@ -39,6 +39,10 @@ def main():
     ap.add_argument("--dim", type=int, default=3)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--families", default="all")
+    ap.add_argument("--matrix", default="poisson", choices=["poisson", "diffusion27", "sa_coarse"],
+                    help="poisson: 7-/5-point Poisson n^dim; diffusion27: the 27-point variable-coefficient operator of "
+                         "BASELINE config 4 (plain CSR: nothing repeats); sa_coarse: level 1 of its smoothed-aggregation "
+                         "hierarchy (50-60 nnz/row)")
     args = ap.parse_args()
     sp.init(0)
     stream = torch.cuda.Stream()
@@ -49,8 +53,20 @@ def main():
     except Exception:
         pass
     t0 = time.time()
-    A = generators.poisson_7pt(args.n, args.n, args.n) if args.dim == 3 else generators.poisson_5pt(args.n, args.n)
-    print(f"# matrix {args.dim}D n={A.nrow} nnz={A.nnz} generated in {time.time()-t0:.1f}s", flush=True)
+    if args.matrix == "poisson":
+        A = generators.poisson_7pt(args.n, args.n, args.n) if args.dim == 3 else generators.poisson_5pt(args.n, args.n)
+    else:
+        from sparsh_amg_b200 import host
+
+        host.set_options(threads=os.cpu_count() or 1, max_levels=32, print_setup=0, print_solve=0, coarsening=2)
+        D = host.HostMatrix.diffusion27(args.n, args.n, args.n)
+        if args.matrix == "diffusion27":
+            A = generators.HostCSR(D.nrow, D.nrow, D.rowptr.copy(), D.colindex.copy(), D.val.copy())
+        else:
+            L1 = host.HostAmg(D).levels()[1]["A"]
+            A = generators.HostCSR(L1.nrow, L1.ncol, L1.rowptr.copy(), L1.colindex.copy(), L1.val.copy())
+    print(f"# matrix {args.matrix} {args.dim}D n={A.nrow} nnz={A.nnz} ({A.nnz / A.nrow:.1f} per row) generated in "
+          f"{time.time()-t0:.1f}s", flush=True)
     m, z = A.nrow, A.nnz
     dA = sp.DeviceMatrix.from_csr(A)
     print("# default kernel:", dA.kernel())
