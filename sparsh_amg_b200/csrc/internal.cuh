@@ -44,14 +44,15 @@ struct NvtxRange {
 };
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
-// An iteration is ~250 dependent kernels, most of them a few microseconds long on the small levels: the gap between two
-// graph nodes (drain, launch, CTA scheduling) is a good part of their cost.  Launched with the programmatic-stream-
-// serialisation attribute, kernel k+1 is scheduled as soon as every CTA of kernel k has passed its
-// griddepcontrol.launch_dependents (the first thing our kernels do after their own griddepcontrol.wait) and then blocks
-// in griddepcontrol.wait until kernel k has completed and its memory operations are visible: the launch latency
-// overlaps the predecessor instead of following it.  A kernel launched WITHOUT the attribute passes the wait at once,
-// and a predecessor that never triggers releases its dependents when it exits, so mixing is safe.  Captured into CUDA
-// graphs as programmatic dependency edges.  SPARSH_PDL=0 launches everything classically.
+// An iteration is ~250 dependent kernels, most of them a few microseconds long on the small levels.  Launched with the
+// programmatic-stream-serialisation attribute, kernel k+1 is scheduled as soon as every CTA of kernel k has passed its
+// griddepcontrol.launch_dependents (the first thing our kernels do after their own griddepcontrol.wait; SASS: ACQBULK /
+// PREEXIT) and then blocks in griddepcontrol.wait until kernel k has completed and its memory operations are visible.
+// A kernel launched WITHOUT the attribute passes the wait at once, and a predecessor that never triggers releases its
+// dependents when it exits, so mixing is safe; CUDA graphs capture the attribute as programmatic dependency edges.
+// MEASURED (B200, 256^3, profiles/r02n_*): no gain — 0.1442 s against 0.1446 s on one GPU, 0.0991 s against 0.0961 s on
+// two (inside a CUDA graph the node-to-node gap is already small, and a dependent grid that is resident while it waits
+// takes SM slots from the strips of the other stream).  Hence OFF by default; SPARSH_PDL=1 turns it on.
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

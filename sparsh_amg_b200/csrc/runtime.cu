@@ -26,7 +26,7 @@ static int g_pdl = -1;  // -1: not decided yet
 bool pdl_enabled() {
     if (g_pdl < 0) {
         const char *e = getenv("SPARSH_PDL");
-        g_pdl = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+        g_pdl = e ? (atoi(e) != 0 ? 1 : 0) : 0;
     }
     return g_pdl == 1;
 }
