@@ -721,14 +721,19 @@ int dist_run_graphed(sparsh_dist_s *h, const void *k0, const void *k1, int tag, 
         int rc = body();
         c.capturing = false;
         cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
-        if (rc != SPARSH_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
+        if (rc == SPARSH_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ent->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if ((rc != SPARSH_OK || e != cudaSuccess) && h->tail && h->tail->tail_state == 1) {
+            // the cooperative kernel of the replicated levels (tail.cu) is not capturable here: classical launches instead
+            cudaGetLastError();
+            ent->exec = nullptr;
+            tail_free(h->tail);
+            h->tail->tail_state = 2;
+            return dist_run_graphed(h, k0, k1, tag, body);
         }
+        if (rc != SPARSH_OK) return rc;
         SP_CUDA(e);
         ent->kernels = c.captured;
-        SP_CUDA(cudaGraphInstantiate(&ent->exec, graph, 0));
-        SP_CUDA(cudaGraphDestroy(graph));
     }
     SP_CUDA(cudaGraphLaunch(ent->exec, c.stream));
     c.launches += ent->kernels;

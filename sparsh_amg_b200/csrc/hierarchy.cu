@@ -70,7 +70,10 @@ int enqueue_vcycle(sparsh_hierarchy_s *h, const double *b, double *x, bool x_is_
         T[l] = h->lev[l].tbuf;
         B[l] = l == 0 ? b : h->lev[l].bbuf;
     }
-    for (int l = 0; l < L; l++) {
+    // the levels from `fused` down run as one cooperative kernel (tail.cu); -1: every level launches its own kernels
+    const int fused = tail_level(h);
+    const int bottom = fused >= 0 ? fused : L;
+    for (int l = 0; l < bottom; l++) {
         Level &F = h->lev[l];
         SP_TRY(smooth(h, F, B[l], X[l], T[l], h->prm.pre_sweeps, l > 0 || x_is_zero));
         EpiArgs a;
@@ -82,8 +85,13 @@ int enqueue_vcycle(sparsh_hierarchy_s *h, const double *b, double *x, bool x_is_
         set_error("hierarchy without a coarse solver");
         return SPARSH_ERR_INVALID;
     }
-    SP_TRY(coarse_apply(h->coarse, B[L], X[L]));
-    for (int l = L; l > 0; l--) {
+    if (fused >= 0) {
+        SP_TRY(enqueue_tail(h));
+        X[fused] = h->tail_x;
+    } else {
+        SP_TRY(coarse_apply(h->coarse, B[L], X[L]));
+    }
+    for (int l = bottom; l > 0; l--) {
         Level &F = h->lev[l - 1];
         SP_TRY(launch_csr(F.P, EPI_PROLONG, X[l], X[l - 1], EpiArgs(), 0, F.n));
         SP_TRY(smooth(h, F, B[l - 1], X[l - 1], T[l - 1], h->prm.post_sweeps, false));
@@ -254,6 +262,7 @@ int sparsh_hierarchy_destroy(sparsh_hierarchy_t h) {
         cudaFree(L.rbuf);
     }
     coarse_free(&h->coarse);
+    tail_free(h);
     for (int i = 0; i < 8; i++) cudaFree(h->kv[i]);
     cudaFree(h->d_sc);
     cudaFreeHost(h->h_sc);

@@ -574,6 +574,44 @@ def test_graph_and_direct_launch_agree_bitwise(sp, oracle, fixture_system):
     np.testing.assert_array_equal(out[0][2], out[1][2])
 
 
+def test_fused_tail_kernel_is_bit_identical(sp, oracle, monkeypatch):
+    """the small levels of the cycle as ONE cooperative kernel (csrc/tail.cu) against the same levels launched kernel by
+    kernel: V-cycle, AMG-PCG and BiCGStab leave the same bits behind (HEM and Beck hierarchies, graph and direct mode),
+    and both agree with the oracle"""
+    A = oracle.gen_poisson3d(40, 36, 32)
+    b = np.ones(A.nrow)
+    xr = np.random.default_rng(9).standard_normal(A.nrow)
+    for coarsening in (0, 1):
+        amg = OracleAmg(A, coarsening=coarsening, limit_upper=400, limit_lower=200)
+        levels = amg.hierarchy().levels
+        assert len(levels) >= 4
+        out = {}
+        for rows in ("0", "131072"):
+            monkeypatch.setenv("SPARSH_TAIL_ROWS", rows)
+            for graph in (True, False):
+                dH = sp.DeviceHierarchy(levels, use_graph=graph)
+                db = sp.DeviceVector(data=b)
+                v = dH.vcycle(db, sp.DeviceVector(data=xr), 2).download()
+                dx = sp.DeviceVector(A.nrow).fill(0.0)
+                it, hist, ok = dH.pcg(db, dx, 1e-8)
+                dy = sp.DeviceVector(A.nrow).fill(0.0)
+                itb, histb, okb = dH.pbicgstab(db, dy, 1e-8)
+                assert ok and okb
+                out[(rows, graph)] = (v, it, hist, dx.download(), itb, histb, dy.download())
+        ref = out[("0", True)]
+        for key, got in out.items():
+            np.testing.assert_array_equal(got[0], ref[0])
+            assert got[1] == ref[1] and got[4] == ref[4]
+            np.testing.assert_array_equal(got[2], ref[2])
+            np.testing.assert_array_equal(got[3], ref[3])
+            np.testing.assert_array_equal(got[5], ref[5])
+            np.testing.assert_array_equal(got[6], ref[6])
+        _, want = amg.pcg(b, np.zeros(A.nrow), 1e-8)
+        assert ref[1] == len(want) - 1
+        assert_hist(ref[2], want)
+    monkeypatch.delenv("SPARSH_TAIL_ROWS")
+
+
 def test_sweep_count_and_zero_guess_semantics(sp, oracle, fixture_system):
     """6 sweeps = the reference GPU path's count; x_is_zero must equal an explicit zero vector."""
     A, b = fixture_system
