@@ -1,4 +1,4 @@
-// tail.cu — the small levels of a V-cycle as ONE cooperative kernel.
+// tail.cu — the small levels of a V-cycle as ONE kernel (cooperative grid, or one thread-block cluster).
 //
 // Below ~10^5 rows a level's operator applications are a few microseconds of work each, and the gap between two graph
 // nodes (drain, launch, CTA scheduling: ~3 us) costs as much as the work: on the 14-level hierarchy of 3D Poisson 256^3
@@ -41,8 +41,11 @@ __device__ __forceinline__ double row_sum(const TailOp &op, int row) {
     return s;
 }
 
+// CLUSTER = false: cooperative launch, one CTA per SM, grid barrier between operations.
+// CLUSTER = true : ONE thread-block cluster of 16 CTAs (non-portable size) and the hardware cluster barrier
+//                  (barrier.cluster, ~0.2 us) between operations — for the levels small enough for 16 SMs.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(TAIL_T) tail_cycle_kernel(const TailOp *__restrict__ ops, int nops) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = blockIdx.x * TAIL_T + threadIdx.x, nthreads = gridDim.x * TAIL_T;
     for (int o = 0; o < nops; o++) {
         const TailOp op = ops[o];
@@ -93,16 +96,29 @@ __global__ void __launch_bounds__(TAIL_T) tail_cycle_kernel(const TailOp *__rest
                 }
             }
         }
-        grid.sync();
+        if (CLUSTER)
+            cooperative_groups::this_cluster().sync();  // release/acquire at cluster scope: the CTAs' global writes are ordered
+        else
+            cooperative_groups::this_grid().sync();
     }
 }
 
 }  // namespace
 
-// levels with at most this many rows go into the cooperative kernel (SPARSH_TAIL_ROWS; 0 switches it off)
-static int tail_rows() {  // read when a hierarchy takes its decision (once per hierarchy), so tests can compare both ways
+// SPARSH_TAIL_MODE: 0 (default) every level launches its own kernels; 1 the levels with at most SPARSH_TAIL_ROWS rows
+// (default 131072) run as one cooperative kernel; 2 the levels with at most SPARSH_TAIL_ROWS rows (default 32768) run as one
+// 16-CTA cluster.  Read when a hierarchy takes its decision (once per hierarchy), so tests can compare the variants.
+// MEASURED (B200, 256^3, profiles/r02o_*): mode 1 removes 45 % of the launches of a solve and is bit-identical, but is no
+// faster — 0.1457 s against 0.1443 s on one GPU, 0.0982 s against 0.0963 s on two: inside a CUDA graph a kernel boundary
+// costs about what a grid barrier over 128 CTAs costs.  Hence off by default.
+static int tail_mode() {
+    const char *e = getenv("SPARSH_TAIL_MODE");
+    return e ? atoi(e) : 0;
+}
+static int tail_rows() {
     const char *e = getenv("SPARSH_TAIL_ROWS");
-    return e ? atoi(e) : 131072;
+    if (e) return atoi(e);
+    return tail_mode() == 2 ? 32768 : 131072;
 }
 
 // first level of the fused bottom (>= 1: level 0 works on the caller's vectors), or -1
@@ -111,15 +127,20 @@ int tail_level(sparsh_hierarchy_s *h) {
     if (h->tail_state == 1) return h->tail_first;
     h->tail_state = 2;
     const int L = (int)h->lev.size() - 1;
-    if (tail_rows() <= 0 || h->prm.smoother != 0 || L < 1 || h->coarse.n == 0) return -1;
+    if (tail_mode() <= 0 || tail_rows() <= 0 || h->prm.smoother != 0 || L < 1 || h->coarse.n == 0) return -1;
     int first = L;  // the coarsest level alone is not worth it: need at least one smoothed level
     while (first > 1 && h->lev[first - 1].n <= tail_rows()) first--;
     if (first >= L) return -1;
     // only CSR kernels that evaluate a row left to right are reproduced bit for bit: no vector-family matrices below
     for (int l = first; l < L; l++)
         if (h->lev[l].A->kind == KIND_VECTOR || h->lev[l].P->kind == KIND_VECTOR || h->lev[l].R->kind == KIND_VECTOR) return -1;
+    const bool cluster = tail_mode() == 2;
     int coop = 0;
-    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx().device) != cudaSuccess || !coop) return -1;
+    if (!cluster && (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx().device) != cudaSuccess || !coop)) return -1;
+    if (cluster && cudaFuncSetAttribute(tail_cycle_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
     // the program: the operations enqueue_vcycle would launch for levels first..L, with its ping-pong bookkeeping
     std::vector<TailOp> prog;
     auto mat = [](TailOp &op, const sparsh_matrix_s *M) {
@@ -200,13 +221,14 @@ int tail_level(sparsh_hierarchy_s *h) {
         smooth(l - 1, h->prm.post_sweeps, false);
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tail_cycle_kernel, TAIL_T, 0) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tail_cycle_kernel<false>, TAIL_T, 0) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return -1;
     }
-    // enough CTAs for a row per thread on the largest fused level, never more than one per SM (all co-resident)
+    // enough CTAs for a row per thread on the largest fused level, never more than one per SM (all co-resident);
+    // cluster mode: exactly one cluster of 16 CTAs
     const int want = (h->lev[first].n + TAIL_T - 1) / TAIL_T;
-    h->tail_grid = std::max(1, std::min(want, ctx().sm_count));
+    h->tail_grid = cluster ? -16 : std::max(1, std::min(want, ctx().sm_count));
     if (cudaMalloc(&h->tail_prog, sizeof(TailOp) * prog.size()) != cudaSuccess ||
         cudaMemcpy(h->tail_prog, prog.data(), sizeof(TailOp) * prog.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError();
@@ -224,8 +246,23 @@ int enqueue_tail(sparsh_hierarchy_s *h) {
     Context &c = ctx();
     const TailOp *prog = static_cast<const TailOp *>(h->tail_prog);
     int nops = h->tail_nops;
-    void *args[] = {(void *)&prog, (void *)&nops};
-    SP_CUDA(cudaLaunchCooperativeKernel((const void *)tail_cycle_kernel, dim3(h->tail_grid), dim3(TAIL_T), args, 0, c.stream));
+    if (h->tail_grid < 0) {  // one cluster of -tail_grid CTAs: an ordinary (capturable) launch with a cluster dimension
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(-h->tail_grid);
+        cfg.blockDim = dim3(TAIL_T);
+        cfg.stream = c.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)(-h->tail_grid);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SP_CUDA(cudaLaunchKernelEx(&cfg, tail_cycle_kernel<true>, prog, nops));
+    } else {
+        void *args[] = {(void *)&prog, (void *)&nops};
+        SP_CUDA(cudaLaunchCooperativeKernel((const void *)tail_cycle_kernel<false>, dim3(h->tail_grid), dim3(TAIL_T), args, 0, c.stream));
+    }
     count_launch();
     return SPARSH_OK;
 }

@@ -575,8 +575,8 @@ def test_graph_and_direct_launch_agree_bitwise(sp, oracle, fixture_system):
 
 
 def test_fused_tail_kernel_is_bit_identical(sp, oracle, monkeypatch):
-    """the small levels of the cycle as ONE cooperative kernel (csrc/tail.cu) against the same levels launched kernel by
-    kernel: V-cycle, AMG-PCG and BiCGStab leave the same bits behind (HEM and Beck hierarchies, graph and direct mode),
+    """the small levels of the cycle as ONE kernel (csrc/tail.cu: cooperative grid, or one 16-CTA cluster) against the same
+    levels launched kernel by kernel: V-cycle, AMG-PCG and BiCGStab leave the same bits behind (HEM and Beck hierarchies, graph and direct mode),
     and both agree with the oracle"""
     A = oracle.gen_poisson3d(40, 36, 32)
     b = np.ones(A.nrow)
@@ -586,8 +586,8 @@ def test_fused_tail_kernel_is_bit_identical(sp, oracle, monkeypatch):
         levels = amg.hierarchy().levels
         assert len(levels) >= 4
         out = {}
-        for rows in ("0", "131072"):
-            monkeypatch.setenv("SPARSH_TAIL_ROWS", rows)
+        for mode in ("0", "1", "2"):  # per-kernel launches, cooperative grid, 16-CTA cluster
+            monkeypatch.setenv("SPARSH_TAIL_MODE", mode)
             for graph in (True, False):
                 dH = sp.DeviceHierarchy(levels, use_graph=graph)
                 db = sp.DeviceVector(data=b)
@@ -597,7 +597,7 @@ def test_fused_tail_kernel_is_bit_identical(sp, oracle, monkeypatch):
                 dy = sp.DeviceVector(A.nrow).fill(0.0)
                 itb, histb, okb = dH.pbicgstab(db, dy, 1e-8)
                 assert ok and okb
-                out[(rows, graph)] = (v, it, hist, dx.download(), itb, histb, dy.download())
+                out[(mode, graph)] = (v, it, hist, dx.download(), itb, histb, dy.download())
         ref = out[("0", True)]
         for key, got in out.items():
             np.testing.assert_array_equal(got[0], ref[0])
@@ -609,7 +609,7 @@ def test_fused_tail_kernel_is_bit_identical(sp, oracle, monkeypatch):
         _, want = amg.pcg(b, np.zeros(A.nrow), 1e-8)
         assert ref[1] == len(want) - 1
         assert_hist(ref[2], want)
-    monkeypatch.delenv("SPARSH_TAIL_ROWS")
+    monkeypatch.delenv("SPARSH_TAIL_MODE")
 
 
 def test_sweep_count_and_zero_guess_semantics(sp, oracle, fixture_system):
