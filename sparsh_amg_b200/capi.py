@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("SPARSH_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libsparsh_b200.so")  # (override: kernel experiments)
+LIB_PATH = os.path.join(_HERE, "lib", "libsparsh_b200.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)

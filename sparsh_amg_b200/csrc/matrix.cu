@@ -854,10 +854,8 @@ int sparsh_matrix_kernel_name(sparsh_matrix_t A, int epi, char *buf, size_t len)
         case KIND_PATTERN:
             if (pattern_lean_applies(A)) {
                 const bool div = epi == EPI_JACOBI || epi == EPI_SOR;
-                if (A->threads_forced)
-                    std::snprintf(tmp, sizeof tmp, "csr_pat2_kernel<%d,rpt,%d,%s>", A->threads, A->pat0.len, epis[epi]);
-                else
-                    std::snprintf(tmp, sizeof tmp, "csr_pat2_kernel<%d,%d,%d,%s>", div ? 256 : 128, div ? 1 : 2, A->pat0.len, epis[epi]);
+                const bool one_row = A->threads_forced ? A->threads == 256 : div;
+                std::snprintf(tmp, sizeof tmp, "csr_pat2_kernel<%d,%d,%d,%s>", one_row ? 256 : 128, one_row ? 1 : 2, A->pat0.len, epis[epi]);
             } else {
                 std::snprintf(tmp, sizeof tmp, "csr_pattern_kernel<%d,4,2,%s>", A->threads, epis[epi]);
             }

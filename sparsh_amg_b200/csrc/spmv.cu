@@ -540,16 +540,6 @@ static int launch_stream(const sparsh_matrix_s *A, const double *x, double *y, c
     return finish_launch<EPI>(grid, args);
 }
 
-// rows per thread of the csr-dict16 kernel (SPARSH_DICT_RPT = 2 | 4 | 8 overrides the default for experiments)
-static int dict_rpt() {
-    static const int v = [] {
-        const char *e = getenv("SPARSH_DICT_RPT");
-        const int r = e ? atoi(e) : 4;
-        return (r == 2 || r == 4 || r == 8) ? r : 4;
-    }();
-    return v;
-}
-
 template <int THREADS, int RPT, int EPI>
 static int launch_dict_rpt(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, LaunchDesc d) {
     Context &c = ctx();
@@ -578,34 +568,10 @@ static int launch_dict_rpt(const sparsh_matrix_s *A, const double *x, double *y,
     return finish_launch<EPI>(grid, args);
 }
 
+// 4 rows per thread: measured best of 2 / 4 / 8 on B200 (256^3 Jacobi sweep: 0.180 ms)
 template <int THREADS, int EPI>
 static int launch_dict(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
-    switch (dict_rpt()) {
-        case 2:
-            return launch_dict_rpt<THREADS, 2, EPI>(A, x, y, args, d);
-        case 8:
-            return launch_dict_rpt<THREADS, 8, EPI>(A, x, y, args, d);
-        default:
-            return launch_dict_rpt<THREADS, 4, EPI>(A, x, y, args, d);
-    }
-}
-
-// rows per thread and entries per row per step of the csr-pattern8 kernel (SPARSH_PATTERN_RPT = 2 | 4 | 8 and
-// SPARSH_PATTERN_JB = 2 | 4 override the defaults for experiments)
-static int pattern_rpt() {
-    static const int v = [] {
-        const char *e = getenv("SPARSH_PATTERN_RPT");
-        const int r = e ? atoi(e) : 4;
-        return (r == 2 || r == 4 || r == 8) ? r : 4;
-    }();
-    return v;
-}
-static int pattern_jb() {
-    static const int v = [] {
-        const char *e = getenv("SPARSH_PATTERN_JB");
-        return (e && atoi(e) == 4) ? 4 : 2;
-    }();
-    return v;
+    return launch_dict_rpt<THREADS, 4, EPI>(A, x, y, args, d);
 }
 
 template <int THREADS, int RPT, int JB, int EPI>
@@ -666,19 +632,9 @@ static int launch_pattern(const sparsh_matrix_s *A, const double *x, double *y, 
         return launch_pattern_tma<EPI>(A, x, y, args, d);
     // lean variant (spmv_pattern.cu): one dominant pattern, gathers issued before the pattern byte is known
     if (!pattern_tma() && pattern_lean_applies(A)) return launch_pattern_lean(A, EPI, x, y, args, d);
-    const int rpt = pattern_rpt();
-    if (pattern_jb() == 4) {
-        if (rpt == 2) return launch_pattern_cfg<THREADS, 2, 4, EPI>(A, x, y, args, d);
-        return launch_pattern_cfg<THREADS, 4, 4, EPI>(A, x, y, args, d);  // 8 rows x 4 entries would spill
-    }
-    switch (rpt) {
-        case 2:
-            return launch_pattern_cfg<THREADS, 2, 2, EPI>(A, x, y, args, d);
-        case 8:
-            return launch_pattern_cfg<THREADS, 8, 2, EPI>(A, x, y, args, d);
-        default:
-            return launch_pattern_cfg<THREADS, 4, 2, EPI>(A, x, y, args, d);
-    }
+    // first csr-pattern8 kernel (table in shared memory), 4 rows x 2 entries in flight per thread: the best of the
+    // shapes swept in round 2 (profiles/r02_pattern_sweep_256cubed.log); reached when the lean variant does not apply
+    return launch_pattern_cfg<THREADS, 4, 2, EPI>(A, x, y, args, d);
 }
 
 template <int EPI>

@@ -229,12 +229,9 @@ __device__ __forceinline__ double load_x(const double *x, int c) {
 // CTAs never reference one.  (halo_begin is kept for kernels that want to tell the two apart.)
 template <bool COHERENT, bool DIST>
 __device__ __forceinline__ double load_xd(const double *x, int c, int /*halo_begin*/) {
-#ifdef SPARSH_EXPERIMENT_PLAIN_LOADS  // experiment: what do plain loads cost the single-GPU kernels?
-    return x[c];
-#else
+    // (measured: plain loads cost the single-GPU kernels nothing — profiles/r02g_pattern_lean_v3_sweep.log, PLAIN rows)
     if (COHERENT || DIST) return x[c];
     return __ldg(x + c);
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -176,35 +176,15 @@ int launch_cfg(const sparsh_matrix_s *A, const double *x, double *y, const EpiAr
     return SPARSH_OK;
 }
 
-// rows per thread (SPARSH_PAT2_RPT = 1 | 2 | 4 overrides the default for experiments)
-int lean_rpt() {
-    static const int v = [] {
-        const char *e = getenv("SPARSH_PAT2_RPT");
-        const int r = e ? atoi(e) : 2;
-        return (r == 1 || r == 2 || r == 4) ? r : 2;
-    }();
-    return v;
-}
-
 template <int LEN0, int EPI>
 int launch_len(const sparsh_matrix_s *A, const double *x, double *y, const EpiArgs &args, const LaunchDesc &d) {
-    // measured on B200, 3D Poisson 256^3 (profiles/r02g_pattern_lean_v3_sweep.log): the sweeps with a division in the
-    // epilogue (Jacobi, SOR) are fastest with one row per thread (256 x 1: 0.111 ms), the others with two (128 x 2:
-    // SpMV 0.081 ms); SPARSH_PAT2_RPT / sparsh_matrix_force_kernel(KIND_PATTERN, threads) override for experiments
-    static const bool forced = getenv("SPARSH_PAT2_RPT") != nullptr;
-    if (!forced && !A->threads_forced) {
-        if (EPI == EPI_JACOBI || EPI == EPI_SOR) return launch_cfg<256, 1, LEN0, EPI>(A, x, y, args, d);
-        return launch_cfg<128, 2, LEN0, EPI>(A, x, y, args, d);
-    }
-    const int rpt = lean_rpt();
-    if (A->threads == 128) {
-        if (rpt == 1) return launch_cfg<128, 1, LEN0, EPI>(A, x, y, args, d);
-        if (rpt == 4) return launch_cfg<128, 4, LEN0, EPI>(A, x, y, args, d);
-        return launch_cfg<128, 2, LEN0, EPI>(A, x, y, args, d);
-    }
-    if (rpt == 1) return launch_cfg<256, 1, LEN0, EPI>(A, x, y, args, d);
-    if (rpt == 4) return launch_cfg<256, 4, LEN0, EPI>(A, x, y, args, d);
-    return launch_cfg<256, 2, LEN0, EPI>(A, x, y, args, d);
+    // measured on B200, 3D Poisson 256^3 (profiles/r02g_pattern_lean_v3_sweep.log, r02n_kernel_probe.log): the sweeps
+    // with a division in the epilogue (Jacobi, SOR) are fastest with one row per thread (256 x 1: 0.107 ms), the others
+    // with two (128 x 2: SpMV 0.081 ms).  sparsh_matrix_force_kernel(KIND_PATTERN, threads) pins the CTA size (tests):
+    // 256 -> 256 x 1, 128 -> 128 x 2 for every epilogue.
+    const bool one_row = A->threads_forced ? A->threads == 256 : (EPI == EPI_JACOBI || EPI == EPI_SOR);
+    if (one_row) return launch_cfg<256, 1, LEN0, EPI>(A, x, y, args, d);
+    return launch_cfg<128, 2, LEN0, EPI>(A, x, y, args, d);
 }
 
 template <int EPI>

@@ -24,6 +24,21 @@ def test_reference_arm_prints_contract_line():
     assert line["gpu_launches"] == 0 and line["value"] > 0
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_reference_arm_runs_a_converged_solve_in_its_warmup():
+    """with --warmup >= 1 the reference arm runs ONE solve to convergence with the reference's own stopping rule and
+    extrapolates its bounded samples with THAT iteration count (same config dict as the product arm)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "24",
+                          "--steps", "2", "--warmup", "1", "--ref-iters", "2"], capture_output=True, text=True,
+                         timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    conv = line["details"]["converged_solve"]
+    assert conv["iterations"] >= 5 and conv["final_rel_residual"] <= 1e-8 and conv["seconds"] > 0
+    assert abs(line["value"] - line["details"]["seconds_per_pcg_iteration"] * conv["iterations"]) < 1e-12
+    assert set(line["config"]) == {"workload", "grid", "rows", "nnz"} and line["config"]["rows"] == 24 ** 3
+
+
 def test_reference_arm_non_zero_ranks_do_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))

@@ -3,8 +3,8 @@
 Times the SpMV-family kernels and BLAS-1 on synthetic Poisson matrices with CUDA events on the library's stream and
 prints achieved algorithmic GB/s (SURVEY §8d byte model) per kernel family.  Usage:
     python tools/perf_probe.py [--n 256] [--dim 3] [--reps 20] [--families all|default]
-The experimental csr-pattern8 kernel is probed when the twin exists: run with SPARSH_PATTERN=2 (and
-SPARSH_PATTERN_RPT=2|4|8, SPARSH_PATTERN_JB=2|4 for its launch shapes).
+The csr-pattern8 kernels are probed when the twin exists (default; SPARSH_PAT2=0 selects the first kernel instead of the
+lean one).  The dict families need SPARSH_DICT=2 (the dict twin is not built where csr-pattern8 is selected).
 """
 import argparse
 import json
