@@ -120,11 +120,15 @@ int sparsh_pattern_windows(int n_ent, const int *ent_off, int *tile, int *nwin, 
  * traversal order and unfused arithmetic, columns sorted: row pointers and column indices equal the reference's, values
  * equal this repository's host product bit for bit.  On return *out holds the product on the device and *nnz_coarse its
  * entry count; *out == NULL with SPARSH_OK means "not applicable" (a product row longer than the kernel's per-thread
- * list: use the host product).  sparsh_rap_fetch copies it into caller arrays (rowptr[ncoarse+1], colindex, val). */
+ * list: use the host product).  sparsh_rap_fetch copies it into caller arrays (rowptr[ncoarse+1], colindex, val).
+ * sparsh_galerkin_rap_next computes the next level's product with the fine matrix taken from `fine`, a product that is
+ * still on the device (the coarse matrix of one level is the fine matrix of the next: only P is uploaded). */
 typedef struct sparsh_rap_s *sparsh_rap_t;
 int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, const double *h_val, int ncoarse,
                         const int *h_p_rowptr, const int *h_p_colindex, const double *h_p_val, sparsh_rap_t *out,
                         int *nnz_coarse);
+int sparsh_galerkin_rap_next(sparsh_rap_t fine, int ncoarse, const int *h_p_rowptr, const int *h_p_colindex,
+                             const double *h_p_val, sparsh_rap_t *out, int *nnz_coarse);
 int sparsh_rap_fetch(sparsh_rap_t h, int *h_rowptr, int *h_colindex, double *h_val);
 int sparsh_rap_destroy(sparsh_rap_t h);
 

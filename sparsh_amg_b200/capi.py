@@ -67,6 +67,7 @@ SIGNATURES = {
     "sparsh_pattern_windows": (_i, [_i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, _vp]),
     "sparsh_dict_encode": (_i, [_i, _i, _i, c_int_p, c_int_p, c_dbl_p, _vp, c_dbl_p, c_int_p, c_int_p, c_int_p]),
     "sparsh_galerkin_rap": (_i, [_i, c_int_p, c_int_p, c_dbl_p, _i, c_int_p, c_int_p, c_dbl_p, _vpp, c_int_p]),
+    "sparsh_galerkin_rap_next": (_i, [_vp, _i, c_int_p, c_int_p, c_dbl_p, _vpp, c_int_p]),
     "sparsh_rap_fetch": (_i, [_vp, c_int_p, c_int_p, c_dbl_p]),
     "sparsh_rap_destroy": (_i, [_vp]),
     "sparsh_spmv": (_i, [_vp, _vp, _vp]),

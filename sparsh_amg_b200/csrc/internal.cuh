@@ -319,6 +319,9 @@ int k_scale_inv_sqrt(size_t n, const double *in, const double *d_nrm2, double *o
 // matrix uploads issued by the calling host thread go to `s` (nullptr: the library's stream) — hierarchy.cu builds the
 // levels of a hierarchy with several host threads, each on a stream of its own
 void set_upload_stream(cudaStream_t s);
+// pageable host memory <-> device through the calling thread's pinned staging buffers (matrix.cu)
+int copy_h2d_staged(void *dst, const void *src, size_t bytes, cudaStream_t st);
+int copy_d2h_staged(void *dst, const void *src, size_t bytes, cudaStream_t st);  // returns when the data has arrived
 void release_upload_stage();  // frees the calling thread's pinned staging buffers (matrix.cu)
 
 // ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -68,17 +69,39 @@ struct Stage {
     int next = 0;
     bool ready = false;
 };
-thread_local Stage t_stage;
+// The buffers are expensive to pin, so a thread borrows a pair from a process-wide pool and hands it back when it ends
+// (release_upload_stage): the upload threads of successive calls reuse the same few pairs.
+std::mutex g_stage_mutex;
+std::vector<Stage *> g_stage_pool;  // idle pairs, every copy out of them complete
+constexpr size_t STAGE_POOL_KEEP = 8;
+thread_local Stage *t_stage = nullptr;
+void stage_destroy(Stage *s) {
+    for (int k = 0; k < 2; k++) {
+        if (s->buf[k]) cudaFreeHost(s->buf[k]);
+        if (s->ev[k]) cudaEventDestroy(s->ev[k]);
+    }
+    delete s;
+}
 bool stage_init() {
-    Stage &s = t_stage;
-    if (s.ready) return true;
+    if (t_stage) return true;
+    {
+        std::lock_guard<std::mutex> g(g_stage_mutex);
+        if (!g_stage_pool.empty()) {
+            t_stage = g_stage_pool.back();
+            g_stage_pool.pop_back();
+            return true;
+        }
+    }
+    Stage *s = new Stage();
     for (int k = 0; k < 2; k++)
-        if (cudaHostAlloc(&s.buf[k], STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.ev[k], cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaHostAlloc(&s->buf[k], STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev[k], cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
+            stage_destroy(s);
             return false;
         }
-    s.ready = true;
+    s->ready = true;
+    t_stage = s;
     return true;
 }
 int staged_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
@@ -86,7 +109,7 @@ int staged_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
         SP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return SPARSH_OK;
     }
-    Stage &s = t_stage;
+    Stage &s = *t_stage;
     for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
         const size_t n = std::min(STAGE_BYTES, bytes - off);
         const int k = s.next;
@@ -96,6 +119,38 @@ int staged_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
         SP_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, s.buf[k], n, cudaMemcpyHostToDevice, st));
         SP_CUDA(cudaEventRecord(s.ev[k], st));
         s.used[k] = true;
+    }
+    return SPARSH_OK;
+}
+
+// device -> pageable host array through the same pair of buffers (chunk k is copied out of its buffer while chunk k+1
+// is on its way); the call returns when everything has arrived
+int staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes < ((size_t)1 << 20) || !stage_init()) {
+        SP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        SP_CUDA(cudaStreamSynchronize(st));
+        return SPARSH_OK;
+    }
+    Stage &s = *t_stage;
+    for (int k = 0; k < 2; k++)
+        if (s.used[k]) SP_CUDA(cudaEventSynchronize(s.ev[k]));  // no upload of this thread still reads the buffers
+    size_t issued = 0, drained = 0;
+    int kin = 0, kout = 0;
+    size_t len[2] = {0, 0};
+    while (drained < bytes) {
+        while (issued < bytes && issued - drained < 2 * STAGE_BYTES) {
+            const size_t n = std::min(STAGE_BYTES, bytes - issued);
+            SP_CUDA(cudaMemcpyAsync(s.buf[kin], static_cast<const char *>(src) + issued, n, cudaMemcpyDeviceToHost, st));
+            SP_CUDA(cudaEventRecord(s.ev[kin], st));
+            s.used[kin] = true;
+            len[kin] = n;
+            issued += n;
+            kin ^= 1;
+        }
+        SP_CUDA(cudaEventSynchronize(s.ev[kout]));
+        std::memcpy(static_cast<char *>(dst) + drained, s.buf[kout], len[kout]);
+        drained += len[kout];
+        kout ^= 1;
     }
     return SPARSH_OK;
 }
@@ -659,14 +714,27 @@ int validate(int nrow, int ncol, int nnz, const int *rp, const int *ci) {
 
 namespace sparsh {
 void set_upload_stream(cudaStream_t s) { t_upload_stream = s; }
+int copy_h2d_staged(void *dst, const void *src, size_t bytes, cudaStream_t st) { return staged_h2d(dst, src, bytes, st); }
+int copy_d2h_staged(void *dst, const void *src, size_t bytes, cudaStream_t st) { return staged_d2h(dst, src, bytes, st); }
 // give this thread's pinned staging buffers back (upload worker threads call it before they end)
 void release_upload_stage() {
-    Stage &s = t_stage;
-    for (int k = 0; k < 2; k++) {
-        if (s.buf[k]) cudaFreeHost(s.buf[k]);
-        if (s.ev[k]) cudaEventDestroy(s.ev[k]);
+    Stage *s = t_stage;
+    if (!s) return;
+    t_stage = nullptr;
+    for (int k = 0; k < 2; k++)
+        if (s->used[k]) {
+            cudaEventSynchronize(s->ev[k]);  // the pool holds idle pairs only
+            s->used[k] = false;
+        }
+    s->next = 0;
+    {
+        std::lock_guard<std::mutex> g(g_stage_mutex);
+        if (g_stage_pool.size() < STAGE_POOL_KEEP) {
+            g_stage_pool.push_back(s);
+            return;
+        }
     }
-    s = Stage();
+    stage_destroy(s);
 }
 }  // namespace sparsh
 

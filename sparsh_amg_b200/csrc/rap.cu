@@ -9,7 +9,16 @@
 //   transpose   R = P^T, stable (a coarse row lists its fine rows ascending): count, scan, scatter, per-row sort
 //   spgemm      two passes (count distinct columns per row -> scan -> fill), rows longer than RAP_MAX_ROW entries make the
 //               call report "not applicable" and the host product runs instead (never a silent difference)
+//   transfers   host arrays go through pinned staging buffers on up to four host threads (run_copies); a product can be the
+//               fine matrix of the next one without leaving the device (sparsh_galerkin_rap_next)
 // No cuSPARSE / thrust: the scans and sorts are the few kernels below.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.cuh"
@@ -32,6 +41,14 @@ struct DevCsr {
         rp = ci = nullptr;
         v = nullptr;
     }
+};
+
+// device scratch that is released on every return path
+template <typename T>
+struct Scratch {
+    T *p = nullptr;
+    ~Scratch() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)); }
 };
 
 // ---- exclusive scan: out[0] = 0, out[i + 1] = in[0] + ... + in[i] ------------------------------------------------------
@@ -120,14 +137,12 @@ int exclusive_scan(const int *in, int n, int *out, cudaStream_t st) {
         return SPARSH_OK;
     }
     const int nblocks = (n + SCAN_T * SCAN_ITEMS - 1) / (SCAN_T * SCAN_ITEMS);
-    int *sums = nullptr;
-    SP_CUDA(cudaMalloc(&sums, sizeof(int) * (size_t)nblocks));
-    scan_block_kernel<<<nblocks, SCAN_T, 0, st>>>(in, n, out, sums);
-    scan_sums_kernel<<<1, SCAN_T, 0, st>>>(sums, nblocks);
-    scan_add_kernel<<<nblocks, SCAN_T, 0, st>>>(out, n, sums);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(sums);
-    SP_CUDA(e);
+    Scratch<int> sums;
+    SP_CUDA(sums.alloc((size_t)nblocks));
+    scan_block_kernel<<<nblocks, SCAN_T, 0, st>>>(in, n, out, sums.p);
+    scan_sums_kernel<<<1, SCAN_T, 0, st>>>(sums.p, nblocks);
+    scan_add_kernel<<<nblocks, SCAN_T, 0, st>>>(out, n, sums.p);
+    SP_CUDA(cudaStreamSynchronize(st));  // the scratch is freed on return: the kernels must be done with it
     SP_CUDA(cudaGetLastError());
     return SPARSH_OK;
 }
@@ -172,22 +187,20 @@ int transpose(const DevCsr &M, DevCsr *T, cudaStream_t st) {
     T->nrow = M.ncol;
     T->ncol = M.nrow;
     T->nnz = M.nnz;
-    int *count = nullptr;
+    Scratch<int> count;  // T's arrays belong to the caller's DevCsr, which releases them on every path
     SP_CUDA(cudaMalloc(&T->rp, sizeof(int) * ((size_t)M.ncol + 1)));
     SP_CUDA(cudaMalloc(&T->ci, sizeof(int) * (size_t)std::max(M.nnz, 1)));
     SP_CUDA(cudaMalloc(&T->v, sizeof(double) * (size_t)std::max(M.nnz, 1)));
-    SP_CUDA(cudaMalloc(&count, sizeof(int) * (size_t)std::max(M.ncol, 1)));
-    SP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)std::max(M.ncol, 1), st));
-    if (M.nnz > 0) count_cols_kernel<<<(M.nnz + 255) / 256, 256, 0, st>>>(M.nnz, M.ci, count);
-    int rc = exclusive_scan(count, M.ncol, T->rp, st);
-    if (rc == SPARSH_OK) {
-        cudaMemsetAsync(count, 0, sizeof(int) * (size_t)std::max(M.ncol, 1), st);
-        if (M.nrow > 0) scatter_T_kernel<<<(M.nrow + 255) / 256, 256, 0, st>>>(M.nrow, M.rp, M.ci, M.v, T->rp, count, T->ci, T->v);
-        if (T->nrow > 0) sort_rows_kernel<<<(T->nrow + 255) / 256, 256, 0, st>>>(T->nrow, T->rp, T->ci, T->v);
-        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = SPARSH_ERR_CUDA;
-    }
-    cudaFree(count);
-    return rc;
+    SP_CUDA(count.alloc((size_t)M.ncol));
+    SP_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)std::max(M.ncol, 1), st));
+    if (M.nnz > 0) count_cols_kernel<<<(M.nnz + 255) / 256, 256, 0, st>>>(M.nnz, M.ci, count.p);
+    SP_TRY(exclusive_scan(count.p, M.ncol, T->rp, st));
+    SP_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)std::max(M.ncol, 1), st));
+    if (M.nrow > 0) scatter_T_kernel<<<(M.nrow + 255) / 256, 256, 0, st>>>(M.nrow, M.rp, M.ci, M.v, T->rp, count.p, T->ci, T->v);
+    if (T->nrow > 0) sort_rows_kernel<<<(T->nrow + 255) / 256, 256, 0, st>>>(T->nrow, T->rp, T->ci, T->v);
+    SP_CUDA(cudaStreamSynchronize(st));
+    SP_CUDA(cudaGetLastError());
+    return SPARSH_OK;
 }
 
 // ---- C = A * B, Gustavson, one thread per row ---------------------------------------------------------------------------
@@ -251,23 +264,18 @@ int spgemm(const DevCsr &A, const DevCsr &B, DevCsr *C, bool *applicable, cudaSt
     *applicable = true;
     C->nrow = A.nrow;
     C->ncol = B.ncol;
-    int *count = nullptr, *flag = nullptr;
-    SP_CUDA(cudaMalloc(&count, sizeof(int) * (size_t)std::max(A.nrow, 1)));
-    SP_CUDA(cudaMalloc(&flag, sizeof(int)));
+    Scratch<int> count, flag;
+    SP_CUDA(count.alloc((size_t)A.nrow));
+    SP_CUDA(flag.alloc(1));
     SP_CUDA(cudaMalloc(&C->rp, sizeof(int) * ((size_t)A.nrow + 1)));
-    cudaMemsetAsync(flag, 0, sizeof(int), st);
+    SP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     const int grid = (A.nrow + 127) / 128;
-    if (A.nrow > 0) spgemm_count_kernel<<<grid, 128, 0, st>>>(A.nrow, A.rp, A.ci, B.rp, B.ci, count, flag);
-    int rc = exclusive_scan(count, A.nrow, C->rp, st);
+    if (A.nrow > 0) spgemm_count_kernel<<<grid, 128, 0, st>>>(A.nrow, A.rp, A.ci, B.rp, B.ci, count.p, flag.p);
+    SP_TRY(exclusive_scan(count.p, A.nrow, C->rp, st));
     int h_flag = 0, nnz = 0;
-    if (rc == SPARSH_OK) {
-        cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(&nnz, C->rp + A.nrow, sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess) rc = SPARSH_ERR_CUDA;
-    }
-    cudaFree(count);
-    cudaFree(flag);
-    if (rc != SPARSH_OK) return rc;
+    SP_CUDA(cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaMemcpyAsync(&nnz, C->rp + A.nrow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaStreamSynchronize(st));
     if (h_flag) {
         *applicable = false;
         return SPARSH_OK;
@@ -280,19 +288,85 @@ int spgemm(const DevCsr &A, const DevCsr &B, DevCsr *C, bool *applicable, cudaSt
     return SPARSH_OK;
 }
 
-int upload_csr(int nrow, int ncol, const int *rp, const int *ci, const double *v, DevCsr *M, cudaStream_t st) {
-    M->nrow = nrow;
-    M->ncol = ncol;
-    M->nnz = rp[nrow];
-    SP_CUDA(cudaMalloc(&M->rp, sizeof(int) * ((size_t)nrow + 1)));
-    SP_CUDA(cudaMalloc(&M->ci, sizeof(int) * (size_t)std::max(M->nnz, 1)));
-    SP_CUDA(cudaMalloc(&M->v, sizeof(double) * (size_t)std::max(M->nnz, 1)));
-    SP_CUDA(cudaMemcpyAsync(M->rp, rp, sizeof(int) * ((size_t)nrow + 1), cudaMemcpyHostToDevice, st));
-    if (M->nnz > 0) {
-        SP_CUDA(cudaMemcpyAsync(M->ci, ci, sizeof(int) * (size_t)M->nnz, cudaMemcpyHostToDevice, st));
-        SP_CUDA(cudaMemcpyAsync(M->v, v, sizeof(double) * (size_t)M->nnz, cudaMemcpyHostToDevice, st));
+// ---- pageable host arrays <-> device, a few arrays at a time ------------------------------------------------------------
+// Each job is one contiguous copy through the pinned staging buffers of the thread that runs it (matrix.cu); up to four
+// host threads, each on a stream of its own, share the jobs — one thread's memcpy into (out of) its staging buffer
+// overlaps the DMA of the others, which is what a single pageable cudaMemcpy cannot do.
+struct CopyJob {
+    void *dst;
+    const void *src;
+    size_t bytes;
+    bool to_device;
+};
+int run_copies(std::vector<CopyJob> jobs, cudaStream_t main_stream) {
+    // split large jobs so that the threads end together
+    constexpr size_t PIECE = (size_t)96 << 20;
+    std::vector<CopyJob> pieces;
+    for (const CopyJob &j : jobs)
+        for (size_t off = 0; off < j.bytes; off += PIECE)
+            pieces.push_back(CopyJob{static_cast<char *>(j.dst) + off, static_cast<const char *>(j.src) + off,
+                                     std::min(PIECE, j.bytes - off), j.to_device});
+    if (pieces.empty()) return SPARSH_OK;
+    size_t total = 0;
+    for (const CopyJob &j : pieces) total += j.bytes;
+    int nthreads = total < ((size_t)32 << 20) ? 1 : (int)std::min<size_t>(pieces.size(), 4);
+    if (const char *e = getenv("SPARSH_RAP_COPY_THREADS")) nthreads = std::max(1, std::min(atoi(e), 16));
+    SP_CUDA(cudaStreamSynchronize(main_stream));  // the device side of every job is complete / free to overwrite
+    std::atomic<size_t> next{0};
+    std::atomic<int> first_rc{SPARSH_OK};
+    std::mutex err_mutex;
+    std::string err_msg;
+    const int device = ctx().device;
+    auto worker = [&](bool own_thread) {
+        cudaStream_t st = main_stream;
+        cudaStream_t mine = nullptr;
+        if (own_thread) {
+            cudaSetDevice(device);
+            if (cudaStreamCreateWithFlags(&mine, cudaStreamNonBlocking) == cudaSuccess) st = mine;
+        }
+        for (size_t i = next++; i < pieces.size(); i = next++) {
+            if (first_rc.load() != SPARSH_OK) break;
+            const CopyJob &j = pieces[i];
+            const int rc = j.to_device ? copy_h2d_staged(j.dst, j.src, j.bytes, st) : copy_d2h_staged(j.dst, j.src, j.bytes, st);
+            if (rc != SPARSH_OK) {
+                std::lock_guard<std::mutex> g(err_mutex);
+                int expect = SPARSH_OK;
+                if (first_rc.compare_exchange_strong(expect, rc)) err_msg = sparsh_last_error();
+            }
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            int expect = SPARSH_OK;
+            first_rc.compare_exchange_strong(expect, (int)SPARSH_ERR_CUDA);
+        }
+        if (mine) cudaStreamDestroy(mine);
+        if (own_thread) release_upload_stage();
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, true);
+    worker(false);
+    for (auto &th : pool) th.join();
+    if (first_rc.load() != SPARSH_OK) {
+        set_error(err_msg.empty() ? "device Galerkin product: a copy failed" : err_msg);
+        return first_rc.load();
     }
     return SPARSH_OK;
+}
+
+int alloc_csr(int nrow, int ncol, int nnz, DevCsr *M) {
+    M->nrow = nrow;
+    M->ncol = ncol;
+    M->nnz = nnz;
+    SP_CUDA(cudaMalloc(&M->rp, sizeof(int) * ((size_t)nrow + 1)));
+    SP_CUDA(cudaMalloc(&M->ci, sizeof(int) * (size_t)std::max(nnz, 1)));
+    SP_CUDA(cudaMalloc(&M->v, sizeof(double) * (size_t)std::max(nnz, 1)));
+    return SPARSH_OK;
+}
+void upload_jobs(const DevCsr &M, const int *rp, const int *ci, const double *v, std::vector<CopyJob> *jobs) {
+    jobs->push_back(CopyJob{M.rp, rp, sizeof(int) * ((size_t)M.nrow + 1), true});
+    if (M.nnz > 0) {
+        jobs->push_back(CopyJob{M.ci, ci, sizeof(int) * (size_t)M.nnz, true});
+        jobs->push_back(CopyJob{M.v, v, sizeof(double) * (size_t)M.nnz, true});
+    }
 }
 
 }  // namespace
@@ -305,25 +379,42 @@ struct sparsh_rap_s {
     DevCsr C;  // the Galerkin product on the device, columns sorted
 };
 
-extern "C" {
-
-int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, const double *h_val, int ncoarse,
-                        const int *h_p_rowptr, const int *h_p_colindex, const double *h_p_val, sparsh_rap_t *out,
-                        int *nnz_coarse) {
-    SP_TRY(ensure_init());
-    SP_REQUIRE(nrow >= 0 && ncoarse >= 0 && h_rowptr && h_p_rowptr && out && nnz_coarse, "bad arguments");
+// the product with the fine matrix taken from `fine` (on the device: a previous product) or uploaded from the host arrays
+static int galerkin_product(const DevCsr *fine, int nrow, const int *h_rowptr, const int *h_colindex, const double *h_val,
+                            int ncoarse, const int *h_p_rowptr, const int *h_p_colindex, const double *h_p_val,
+                            sparsh_rap_t *out, int *nnz_coarse) {
     NvtxRange nvtx("sparsh:galerkin-rap");
     cudaStream_t st = ctx().stream;
     *out = nullptr;
     *nnz_coarse = -1;
-    DevCsr A, P, R, AP;
+    DevCsr A_up, P, R, AP;
     sparsh_rap_s *h = new sparsh_rap_s();
     bool ok1 = true, ok2 = true;
-    int rc = upload_csr(nrow, nrow, h_rowptr, h_colindex, h_val, &A, st);
-    if (rc == SPARSH_OK) rc = upload_csr(nrow, ncoarse, h_p_rowptr, h_p_colindex, h_p_val, &P, st);
+    static const bool timing = getenv("SPARSH_SETUP_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing || nrow < 20000) return;
+        cudaStreamSynchronize(st);
+        std::fprintf(stderr, "[rap %d rows] %s at %.3f s\n", nrow, what,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    std::vector<CopyJob> jobs;
+    int rc = SPARSH_OK;
+    if (!fine) {
+        rc = alloc_csr(nrow, nrow, h_rowptr[nrow], &A_up);
+        if (rc == SPARSH_OK) upload_jobs(A_up, h_rowptr, h_colindex, h_val, &jobs);
+    }
+    if (rc == SPARSH_OK) rc = alloc_csr(nrow, ncoarse, h_p_rowptr[nrow], &P);
+    if (rc == SPARSH_OK) upload_jobs(P, h_p_rowptr, h_p_colindex, h_p_val, &jobs);
+    if (rc == SPARSH_OK) rc = run_copies(jobs, st);
+    const DevCsr &A = fine ? *fine : A_up;
+    lap(fine ? "P uploaded (A is on the device)" : "A, P uploaded");
     if (rc == SPARSH_OK) rc = spgemm(A, P, &AP, &ok1, st);                 // A P
+    lap("A P");
     if (rc == SPARSH_OK && ok1) rc = transpose(P, &R, st);                 // R = P^T
+    lap("R = P^T");
     if (rc == SPARSH_OK && ok1) rc = spgemm(R, AP, &h->C, &ok2, st);       // R (A P)
+    lap("R (A P)");
     if (rc == SPARSH_OK && ok1 && ok2) {
         if (h->C.nrow > 0) sort_rows_kernel<<<(h->C.nrow + 255) / 256, 256, 0, st>>>(h->C.nrow, h->C.rp, h->C.ci, h->C.v);
         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
@@ -331,7 +422,7 @@ int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, co
             rc = SPARSH_ERR_CUDA;
         }
     }
-    A.release();
+    A_up.release();
     P.release();
     R.release();
     AP.release();
@@ -345,16 +436,35 @@ int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, co
     return SPARSH_OK;
 }
 
+extern "C" {
+
+int sparsh_galerkin_rap(int nrow, const int *h_rowptr, const int *h_colindex, const double *h_val, int ncoarse,
+                        const int *h_p_rowptr, const int *h_p_colindex, const double *h_p_val, sparsh_rap_t *out,
+                        int *nnz_coarse) {
+    SP_TRY(ensure_init());
+    SP_REQUIRE(nrow >= 0 && ncoarse >= 0 && h_rowptr && h_p_rowptr && out && nnz_coarse, "bad arguments");
+    return galerkin_product(nullptr, nrow, h_rowptr, h_colindex, h_val, ncoarse, h_p_rowptr, h_p_colindex, h_p_val, out,
+                            nnz_coarse);
+}
+
+int sparsh_galerkin_rap_next(sparsh_rap_t fine, int ncoarse, const int *h_p_rowptr, const int *h_p_colindex,
+                             const double *h_p_val, sparsh_rap_t *out, int *nnz_coarse) {
+    SP_TRY(ensure_init());
+    SP_REQUIRE(fine != nullptr && ncoarse >= 0 && h_p_rowptr && out && nnz_coarse, "bad arguments");
+    return galerkin_product(&fine->C, fine->C.nrow, nullptr, nullptr, nullptr, ncoarse, h_p_rowptr, h_p_colindex, h_p_val,
+                            out, nnz_coarse);
+}
+
 int sparsh_rap_fetch(sparsh_rap_t h, int *h_rowptr, int *h_colindex, double *h_val) {
     SP_REQUIRE(h != nullptr && h_rowptr != nullptr, "bad arguments");
-    cudaStream_t st = ctx().stream;
-    SP_CUDA(cudaMemcpyAsync(h_rowptr, h->C.rp, sizeof(int) * ((size_t)h->C.nrow + 1), cudaMemcpyDeviceToHost, st));
+    std::vector<CopyJob> jobs;
+    jobs.push_back(CopyJob{h_rowptr, h->C.rp, sizeof(int) * ((size_t)h->C.nrow + 1), false});
     if (h->C.nnz > 0) {
-        SP_CUDA(cudaMemcpyAsync(h_colindex, h->C.ci, sizeof(int) * (size_t)h->C.nnz, cudaMemcpyDeviceToHost, st));
-        SP_CUDA(cudaMemcpyAsync(h_val, h->C.v, sizeof(double) * (size_t)h->C.nnz, cudaMemcpyDeviceToHost, st));
+        SP_REQUIRE(h_colindex != nullptr && h_val != nullptr, "bad arguments");
+        jobs.push_back(CopyJob{h_colindex, h->C.ci, sizeof(int) * (size_t)h->C.nnz, false});
+        jobs.push_back(CopyJob{h_val, h->C.v, sizeof(double) * (size_t)h->C.nnz, false});
     }
-    SP_CUDA(cudaStreamSynchronize(st));
-    return SPARSH_OK;
+    return run_copies(jobs, ctx().stream);
 }
 
 int sparsh_rap_destroy(sparsh_rap_t h) {

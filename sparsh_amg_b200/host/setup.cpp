@@ -18,6 +18,7 @@
 #include <numeric>
 #include <cstdio>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/sparsh_b200.h"
@@ -569,6 +570,28 @@ void transpose(int nrow, int ncol, const int *rp, const int *ci, const double *v
 
 }  // namespace
 
+// Products that the device computed stay there until the next level has used them as its fine matrix (options().gpu_rap):
+// keyed by the host matrix they were fetched into.  A matrix that is modified afterwards (the colouring reorders it) must
+// be forgotten first.
+namespace {
+std::unordered_map<const sp_matrix_mg *, sparsh_rap_t> g_device_products;
+sparsh_rap_t device_product_of(const sp_matrix_mg *A) {
+    auto it = g_device_products.find(A);
+    return it == g_device_products.end() ? nullptr : it->second;
+}
+void remember_device_product(const sp_matrix_mg *A, sparsh_rap_t h) { g_device_products[A] = h; }
+void forget_device_product(const sp_matrix_mg *A) {
+    auto it = g_device_products.find(A);
+    if (it == g_device_products.end()) return;
+    sparsh_rap_destroy(it->second);
+    g_device_products.erase(it);
+}
+void forget_all_device_products() {
+    for (auto &kv : g_device_products) sparsh_rap_destroy(kv.second);
+    g_device_products.clear();
+}
+}  // namespace
+
 namespace parallel {
 
 // Ac = P^T (A P), columns sorted, diagonal extracted
@@ -579,7 +602,12 @@ void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
     if (options().gpu_rap) {  // same product, computed by the device (csrc/rap.cu): identical integers and values
         sparsh_rap_t rap = nullptr;
         int cnnz = -1;
-        const int rc = sparsh_galerkin_rap(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, &rap, &cnnz);
+        // the fine matrix of this level is the product of the previous one when that is still on the device
+        sparsh_rap_t fine = device_product_of(&A);
+        const int rc = fine ? sparsh_galerkin_rap_next(fine, P1.ncol, P1.rowptr, P1.colindex, P1.val, &rap, &cnnz)
+                            : sparsh_galerkin_rap(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex,
+                                                  P1.val, &rap, &cnnz);
+        forget_device_product(&A);
         if (rc != SPARSH_OK) {
             std::fprintf(stderr, "sparsh_amg: device Galerkin product failed (%d): %s\n", rc, sparsh_last_error());
             std::exit(1);
@@ -595,7 +623,7 @@ void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
                 std::fprintf(stderr, "sparsh_amg: device Galerkin product: fetch failed: %s\n", sparsh_last_error());
                 std::exit(1);
             }
-            sparsh_rap_destroy(rap);
+            remember_device_product(Ac, rap);  // released by the next level's product or at the end of the setup
             Ac->sp_matrix_fill_diagonal();
             if (tm) std::cout << "  RAP on the device: " << omp_get_wtime() - t0 << std::endl;
             return;
@@ -686,6 +714,7 @@ static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
             sequential::HEM_Prolongator(*S.Av[l], S.Pv[l], l);
         parallel::coarsen_matrix(*S.Av[l], S.Av[l + 1], *S.Pv[l]);
         if (colour) {
+            forget_device_product(S.Av[l + 1]);  // the reordering below makes the device copy stale
             S.Av[l + 1]->color_matrix_and_reorder();
             parallel::reorder_prolongator(*S.Av[l + 1], S.Pv[l]);
         }
@@ -693,6 +722,7 @@ static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
         if (S.Av[l]->nrow < o.coarse_lower) break;
     }
     if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
+    forget_all_device_products();
     S.l = l;
     sparsh::last_report().setup_seconds = omp_get_wtime() - t0;
 }

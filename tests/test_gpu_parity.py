@@ -363,11 +363,13 @@ def test_device_galerkin_product(sp, oracle, fixture_system):
         np.testing.assert_array_equal(got[1], want.colindex)
         np.testing.assert_allclose(got[2], want.val, rtol=1e-13, atol=1e-13 * np.abs(want.val).max())
     # a whole hierarchy, host product against device product: identical bits on every level
+    # (the products chain on the device: level l's product is level l+1's fine matrix, sparsh_galerkin_rap_next; the large
+    # grid moves its arrays through the pinned staging buffers on several host threads)
     host.set_options(threads=4, max_levels=32, print_setup=0, coarse_upper=300, coarse_lower=100)
     try:
-        for coarsening in (0, 1, 2):
+        for coarsening, grid in ((0, (24, 20, 18)), (1, (24, 20, 18)), (2, (24, 20, 18)), (0, (112, 96, 80))):
             host.set_options(coarsening=coarsening, gpu_rap=0)
-            M = host.HostMatrix.poisson3d(24, 20, 18)
+            M = host.HostMatrix.poisson3d(*grid)
             h0 = host.HostAmg(M)
             host.set_options(gpu_rap=1)
             h1 = host.HostAmg(M)
