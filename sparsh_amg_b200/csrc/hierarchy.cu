@@ -173,6 +173,22 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
     std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.weight > b.weight; });
     static const bool timing = getenv("SPARSH_UPLOAD_TIMING") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
+    // One slab for everything that lives as long as the hierarchy (internal.cuh: "device memory of a hierarchy"): per CSR
+    // operator the padded arrays, the diagonal, the 1-byte pattern ids and a margin for the small tables; the level
+    // vectors.  A csr-dict16 twin (2 B per entry, only built where csr-pattern8 does not apply) is not counted: it and
+    // anything else beyond the estimate fall through to allocations of their own.
+    if (rc == SPARSH_OK) {
+        auto csr_bytes = [](size_t nrow, size_t nnz) {
+            return 4 * (nrow + 8) + 12 * (nnz + 16) + 8 * (nrow + 1) + (nrow + 16) + ((size_t)1 << 20) + 12 * 256;
+        };
+        size_t total = (size_t)1 << 20;
+        for (int l = 0; l < nlevels; l++) {
+            const sparsh_level_desc &d = levels[l];
+            total += csr_bytes((size_t)d.nrow, (size_t)d.nnz) + 4 * (8 * ((size_t)d.nrow + 2) + 256);
+            if (l < nlevels - 1) total += csr_bytes((size_t)d.nrow, (size_t)d.p_nnz) + csr_bytes((size_t)d.p_ncol, (size_t)d.p_nnz);
+        }
+        h->slab = slab_create(total);  // nullptr (SPARSH_SLAB=0, or no room for one block): individual allocations
+    }
     auto run_task = [&](const Task &t) -> int {
         const sparsh_level_desc &d = levels[t.level];
         Level &L = h->lev[t.level];
@@ -185,12 +201,12 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
             case 2:
                 return sparsh_matrix_create_transpose(d.nrow, d.p_ncol, d.p_nnz, d.p_rowptr, d.p_colindex, d.p_val, &L.R);
             case 3:
-                SP_CUDA(cudaMalloc(&L.tbuf, bytes));
+                SP_CUDA(dev_alloc(&L.tbuf, bytes));
                 if (t.level > 0) {
-                    SP_CUDA(cudaMalloc(&L.xbuf, bytes));
-                    SP_CUDA(cudaMalloc(&L.bbuf, bytes));
+                    SP_CUDA(dev_alloc(&L.xbuf, bytes));
+                    SP_CUDA(dev_alloc(&L.bbuf, bytes));
                 }
-                if (t.level < nlevels - 1) SP_CUDA(cudaMalloc(&L.rbuf, bytes));
+                if (t.level < nlevels - 1) SP_CUDA(dev_alloc(&L.rbuf, bytes));
                 return SPARSH_OK;
             default:
                 return coarse_build_inverse(d.nrow, d.rowptr, d.colindex, d.val, &h->coarse);
@@ -205,6 +221,7 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
         std::string err_msg;
         const int device = ctx().device;
         auto worker = [&](bool own_stream) {
+            slab_bind(h->slab);
             cudaStream_t s = nullptr;
             if (own_stream) {
                 cudaSetDevice(device);  // the runtime's current device is per host thread
@@ -225,6 +242,8 @@ int sparsh_hierarchy_create(int nlevels, const sparsh_level_desc *levels, const 
                 cudaStreamDestroy(s);
             }
             if (own_stream) release_upload_stage();
+            release_thread_scratch();
+            slab_bind(nullptr);
         };
         std::vector<std::thread> pool;
         for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, true);
@@ -256,10 +275,10 @@ int sparsh_hierarchy_destroy(sparsh_hierarchy_t h) {
         sparsh_matrix_destroy(L.A);
         sparsh_matrix_destroy(L.P);
         sparsh_matrix_destroy(L.R);
-        cudaFree(L.xbuf);
-        cudaFree(L.tbuf);
-        cudaFree(L.bbuf);
-        cudaFree(L.rbuf);
+        dev_free(L.xbuf);
+        dev_free(L.tbuf);
+        dev_free(L.bbuf);
+        dev_free(L.rbuf);
     }
     coarse_free(&h->coarse);
     tail_free(h);
@@ -271,6 +290,7 @@ int sparsh_hierarchy_destroy(sparsh_hierarchy_t h) {
     cudaFree(h->gm_V);
     cudaFree(h->gm_d);
     cudaFreeHost(h->gm_h);
+    slab_destroy(h->slab);  // last: the matrices and level vectors above were carved from it
     delete h;
     return SPARSH_OK;
 }

@@ -33,6 +33,7 @@ struct sparsh_hierarchy_s {
     std::vector<sparsh::Level> lev;
     sparsh_params prm;
     sparsh::CoarseInverse coarse;
+    sparsh::DevSlab *slab = nullptr;  // the one device allocation behind the operators and level vectors (internal.cuh)
     // Krylov workspace on level 0 (allocated on first use) and device-resident scalars
     double *kv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_sc = nullptr;  // 16 doubles

@@ -322,7 +322,30 @@ void set_upload_stream(cudaStream_t s);
 // pageable host memory <-> device through the calling thread's pinned staging buffers (matrix.cu)
 int copy_h2d_staged(void *dst, const void *src, size_t bytes, cudaStream_t st);
 int copy_d2h_staged(void *dst, const void *src, size_t bytes, cudaStream_t st);  // returns when the data has arrived
-void release_upload_stage();  // frees the calling thread's pinned staging buffers (matrix.cu)
+void release_upload_stage();  // hands the calling thread's pinned staging buffers back to the pool (matrix.cu)
+
+// ---- device memory of a hierarchy (runtime.cu) ------------------------------------------------------------------------------
+// A device allocation or free is a call into the kernel driver: 0.6-3 ms each on the shared GPU hosts, with 0.1-1 s
+// outliers (tools/alloc_probe.py) — the ~450 of them behind a 13-level hierarchy cost more than moving its 3.7 GB.  So a
+// hierarchy takes ONE slab; the arrays that live as long as it does are carved from the slab by the threads bound to it
+// (bump pointer, 256-byte aligned; dev_free of such a pointer is a no-op, the slab is freed as a whole), and short-lived
+// temporaries come from a grow-only per-thread scratch buffer.  Without a bound slab, or once it is exhausted, dev_alloc
+// is cudaMalloc and dev_free is cudaFree.
+struct DevSlab;
+DevSlab *slab_create(size_t bytes);  // nullptr when the allocation fails: the caller goes on without
+void slab_bind(DevSlab *s);          // the calling thread's dev_alloc calls carve from s; nullptr unbinds
+bool slab_bound();                   // is the calling thread bound to a slab?
+void slab_destroy(DevSlab *s);       // everything carved from the slab dies with it
+cudaError_t dev_alloc_bytes(void **p, size_t bytes);
+template <typename T>
+inline cudaError_t dev_alloc(T **p, size_t bytes) {
+    return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes);
+}
+void dev_free(void *p);
+// at least `bytes` of device memory owned by the calling thread, valid until its next thread_scratch call; the caller
+// synchronises its stream before it lets go of the buffer.  nullptr when the allocation fails.
+void *thread_scratch(size_t bytes);
+void release_thread_scratch();
 
 // ---- dense coarse solve (coarse.cu) ----------------------------------------------------------------------
 struct CoarseInverse {

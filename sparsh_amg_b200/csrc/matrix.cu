@@ -160,9 +160,9 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
     const int n = A->nrow, nnz = A->nnz;
     // padding: the stream kernel's bulk copies round the slice [rowptr[r0], rowptr[r1]) outwards to multiples of 4
     const size_t pad_nnz = (((size_t)nnz + 3) & ~(size_t)3) + 8;
-    SP_CUDA(cudaMalloc(&A->rowptr, sizeof(int) * ((size_t)n + 8)));
-    SP_CUDA(cudaMalloc(&A->col, sizeof(int) * pad_nnz));
-    SP_CUDA(cudaMalloc(&A->val, sizeof(double) * pad_nnz));
+    SP_CUDA(dev_alloc(&A->rowptr, sizeof(int) * ((size_t)n + 8)));
+    SP_CUDA(dev_alloc(&A->col, sizeof(int) * pad_nnz));
+    SP_CUDA(dev_alloc(&A->val, sizeof(double) * pad_nnz));
     SP_CUDA(cudaMemsetAsync(A->col + (nnz & ~3), 0, sizeof(int) * (pad_nnz - (size_t)(nnz & ~3)), c.stream));
     SP_CUDA(cudaMemsetAsync(A->val + (nnz & ~3), 0, sizeof(double) * (pad_nnz - (size_t)(nnz & ~3)), c.stream));
     SP_TRY(staged_h2d(A->rowptr, rp, sizeof(int) * ((size_t)n + 1), c.stream));
@@ -183,7 +183,7 @@ int upload(sparsh_matrix_s *A, const int *rp, const int *ci, const double *v, co
                     }
             diag = dtmp.data();
         }
-        SP_CUDA(cudaMalloc(&A->diag, sizeof(double) * ((size_t)n + 1)));
+        SP_CUDA(dev_alloc(&A->diag, sizeof(double) * ((size_t)n + 1)));
         SP_TRY(staged_h2d(A->diag, diag, sizeof(double) * (size_t)n, c.stream));
     }
     SP_CUDA(cudaStreamSynchronize(c.stream));  // host arrays may be pageable / temporary
@@ -290,9 +290,9 @@ bool build_dict(sparsh_matrix_s *A, const int *rp, const int *ci, const double *
     if (!dict_encode(n, rp, ci, v, code.data(), dv, dof)) return false;
     const size_t pad = ((nnz + 7) & ~(size_t)7) + 16;  // bulk copies round the slice outwards to multiples of 8 codes
     cudaStream_t st = up().stream;
-    if (cudaMalloc(&A->code, sizeof(unsigned short) * pad) != cudaSuccess) return false;
-    cudaMalloc(&A->dict_val, sizeof(double) * 256);
-    cudaMalloc(&A->dict_off, sizeof(int) * 256);
+    if (dev_alloc(&A->code, sizeof(unsigned short) * pad) != cudaSuccess) return false;
+    dev_alloc(&A->dict_val, sizeof(double) * 256);
+    dev_alloc(&A->dict_off, sizeof(int) * 256);
     cudaMemsetAsync(A->code, 0, sizeof(unsigned short) * pad, st);
     cudaMemcpyAsync(A->code, code.data(), sizeof(unsigned short) * nnz, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(A->dict_val, dv.data(), sizeof(double) * dv.size(), cudaMemcpyHostToDevice, st);
@@ -555,21 +555,13 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     const int n = A->nrow;
     if (n == 0 || A->nnz == 0) return false;
     cudaStream_t st = up().stream;
-    PatSlot *d_table = nullptr;
-    int *d_slot_of = nullptr, *d_overflow = nullptr, *d_id_of = nullptr;
-    unsigned long long *d_counts = nullptr;
     bool kept = false;
-    auto cleanup = [&]() {
-        cudaFree(d_table);
-        cudaFree(d_slot_of);
-        cudaFree(d_overflow);
-        cudaFree(d_id_of);
-        cudaFree(d_counts);
+    auto cleanup = [&]() {  // the temporaries live in this thread's scratch buffer; every path here has synchronised st
         if (!kept) {
-            cudaFree(A->pat);
-            cudaFree(A->pat_ent);
-            cudaFree(A->pat_start);
-            cudaFree(A->pat_diag);
+            dev_free(A->pat);
+            dev_free(A->pat_ent);
+            dev_free(A->pat_start);
+            dev_free(A->pat_diag);
             A->pat = nullptr;
             A->pat_ent = nullptr;
             A->pat_start = nullptr;
@@ -577,14 +569,17 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
         }
         cudaGetLastError();
     };
-    bool ok = cudaMalloc(&d_table, sizeof(PatSlot) * PAT_SLOTS) == cudaSuccess &&
-              cudaMalloc(&d_slot_of, sizeof(int) * (size_t)n) == cudaSuccess && cudaMalloc(&d_overflow, sizeof(int) * 2) == cudaSuccess &&
-              cudaMalloc(&d_id_of, sizeof(int) * PAT_SLOTS) == cudaSuccess &&
-              cudaMalloc(&d_counts, sizeof(unsigned long long) * 2) == cudaSuccess;
-    if (!ok) {
-        cleanup();
-        return false;
-    }
+    // temporaries: [table | id_of | slot_of | counts | overflow], each 256-byte aligned, in one scratch block
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_table = 0, o_id = o_table + al(sizeof(PatSlot) * PAT_SLOTS), o_slot = o_id + al(sizeof(int) * PAT_SLOTS),
+                 o_counts = o_slot + al(sizeof(int) * (size_t)n), o_over = o_counts + 256, scratch_bytes = o_over + 256;
+    char *scratch = static_cast<char *>(thread_scratch(scratch_bytes));
+    if (!scratch) return false;
+    PatSlot *d_table = reinterpret_cast<PatSlot *>(scratch + o_table);
+    int *d_id_of = reinterpret_cast<int *>(scratch + o_id), *d_slot_of = reinterpret_cast<int *>(scratch + o_slot);
+    unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(scratch + o_counts);
+    int *d_overflow = reinterpret_cast<int *>(scratch + o_over);
+    bool ok = true;
     std::vector<PatSlot> table(PAT_SLOTS, PatSlot{0ull, 0x7fffffff, 0});
     cudaMemcpyAsync(d_table, table.data(), sizeof(PatSlot) * PAT_SLOTS, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_overflow, 0, sizeof(int) * 2, st);
@@ -641,9 +636,9 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     }
     std::vector<PatEntry> ent((size_t)n_ent + 8, PatEntry{0.0, 0, 0});
     for (int k = 0; k < n_ent; k++) ent[k] = PatEntry{T.val[k], T.off[k], 0};
-    ok = cudaMalloc(&A->pat, (size_t)n + 16) == cudaSuccess && cudaMalloc(&A->pat_ent, sizeof(PatEntry) * ent.size()) == cudaSuccess &&
-         cudaMalloc(&A->pat_start, sizeof(int) * ((size_t)n_pat + 1)) == cudaSuccess &&
-         cudaMalloc(&A->pat_diag, sizeof(double) * (size_t)n_pat) == cudaSuccess;
+    ok = dev_alloc(&A->pat, (size_t)n + 16) == cudaSuccess && dev_alloc(&A->pat_ent, sizeof(PatEntry) * ent.size()) == cudaSuccess &&
+         dev_alloc(&A->pat_start, sizeof(int) * ((size_t)n_pat + 1)) == cudaSuccess &&
+         dev_alloc(&A->pat_diag, sizeof(double) * (size_t)n_pat) == cudaSuccess;
     unsigned long long counts[2] = {0ull, 0ull};
     if (ok) {
         cudaMemsetAsync(A->pat, PAT_ESCAPE, (size_t)n + 16, st);
@@ -687,7 +682,7 @@ bool build_pattern(sparsh_matrix_s *A, const int *rp, const int *ci, const doubl
     {  // x windows for the TMA-staged variant
         PatWindows W = {};
         std::vector<unsigned char> win;
-        if (pattern_windows(T.off, W, win) && cudaMalloc(&A->pat_win, win.size()) == cudaSuccess &&
+        if (pattern_windows(T.off, W, win) && dev_alloc(&A->pat_win, win.size()) == cudaSuccess &&
             cudaMemcpy(A->pat_win, win.data(), win.size(), cudaMemcpyHostToDevice) == cudaSuccess) {
             W.win = A->pat_win;
             A->pat_windows = W;
@@ -783,6 +778,7 @@ int sparsh_matrix_create(int nrow, int ncol, int nnz, const int *h_rowptr, const
         A->threads = 128;
     }
     lap("twins built");
+    if (!slab_bound()) release_thread_scratch();  // a hierarchy build keeps the encoder's scratch until its thread ends
     *out = A;
     return SPARSH_OK;
 }
@@ -858,18 +854,18 @@ int sparsh_matrix_create_transpose(int nrow, int ncol, int nnz, const int *rp, c
 
 int sparsh_matrix_destroy(sparsh_matrix_t A) {
     if (!A) return SPARSH_OK;
-    cudaFree(A->rowptr);
-    cudaFree(A->col);
-    cudaFree(A->val);
-    cudaFree(A->diag);
-    cudaFree(A->code);
-    cudaFree(A->dict_val);
-    cudaFree(A->dict_off);
-    cudaFree(A->pat);
-    cudaFree(A->pat_ent);
-    cudaFree(A->pat_start);
-    cudaFree(A->pat_diag);
-    cudaFree(A->pat_win);
+    dev_free(A->rowptr);
+    dev_free(A->col);
+    dev_free(A->val);
+    dev_free(A->diag);
+    dev_free(A->code);
+    dev_free(A->dict_val);
+    dev_free(A->dict_off);
+    dev_free(A->pat);
+    dev_free(A->pat_ent);
+    dev_free(A->pat_start);
+    dev_free(A->pat_diag);
+    dev_free(A->pat_win);
     delete A;
     return SPARSH_OK;
 }

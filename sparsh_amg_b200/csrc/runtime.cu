@@ -1,8 +1,12 @@
 // runtime.cu — context, streams, memory and BLAS-1 entry points of the C-ABI (include/sparsh_b200.h).
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "internal.cuh"
 
@@ -40,6 +44,87 @@ int ensure_init() {
 }  // namespace sparsh
 
 using namespace sparsh;
+
+// ---- slab / scratch allocation (internal.cuh) -----------------------------------------------------------------------------
+namespace sparsh {
+struct DevSlab {
+    char *base = nullptr;
+    size_t size = 0;
+    std::atomic<size_t> used{0};
+};
+namespace {
+std::mutex g_slab_mutex;
+std::vector<DevSlab *> g_slabs;  // live slabs: dev_free looks a pointer up here
+thread_local DevSlab *t_slab = nullptr;
+thread_local void *t_scratch = nullptr;
+thread_local size_t t_scratch_bytes = 0;
+}  // namespace
+
+DevSlab *slab_create(size_t bytes) {
+    static const bool off = getenv("SPARSH_SLAB") && atoi(getenv("SPARSH_SLAB")) == 0;
+    if (off || bytes == 0) return nullptr;
+    DevSlab *s = new DevSlab();
+    if (cudaMalloc(&s->base, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete s;
+        return nullptr;
+    }
+    s->size = bytes;
+    std::lock_guard<std::mutex> g(g_slab_mutex);
+    g_slabs.push_back(s);
+    return s;
+}
+void slab_bind(DevSlab *s) { t_slab = s; }
+bool slab_bound() { return t_slab != nullptr; }
+void slab_destroy(DevSlab *s) {
+    if (!s) return;
+    {
+        std::lock_guard<std::mutex> g(g_slab_mutex);
+        g_slabs.erase(std::remove(g_slabs.begin(), g_slabs.end(), s), g_slabs.end());
+    }
+    cudaFree(s->base);
+    delete s;
+}
+cudaError_t dev_alloc_bytes(void **p, size_t bytes) {
+    if (DevSlab *s = t_slab) {
+        const size_t need = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+        const size_t at = s->used.fetch_add(need);
+        if (at + need <= s->size) {
+            *p = s->base + at;
+            return cudaSuccess;
+        }
+        s->used.fetch_sub(need);  // exhausted (the estimate was short): an allocation of its own
+    }
+    return cudaMalloc(p, bytes);
+}
+void dev_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_slab_mutex);
+        for (const DevSlab *s : g_slabs)
+            if (static_cast<char *>(p) >= s->base && static_cast<char *>(p) < s->base + s->size) return;
+    }
+    cudaFree(p);
+}
+void *thread_scratch(size_t bytes) {
+    if (bytes <= t_scratch_bytes) return t_scratch;
+    if (t_scratch) cudaFree(t_scratch);
+    t_scratch = nullptr;
+    t_scratch_bytes = 0;
+    if (cudaMalloc(&t_scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        t_scratch = nullptr;
+        return nullptr;
+    }
+    t_scratch_bytes = bytes;
+    return t_scratch;
+}
+void release_thread_scratch() {
+    if (t_scratch) cudaFree(t_scratch);
+    t_scratch = nullptr;
+    t_scratch_bytes = 0;
+}
+}  // namespace sparsh
 
 extern "C" {
 
