@@ -87,13 +87,17 @@ void slab_destroy(DevSlab *s) {
 }
 cudaError_t dev_alloc_bytes(void **p, size_t bytes) {
     if (DevSlab *s = t_slab) {
+        // the bump pointer only ever moves forward (compare-and-swap, never an add that is taken back: a rejected
+        // request must not disturb the offsets concurrent threads are handed)
         const size_t need = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
-        const size_t at = s->used.fetch_add(need);
-        if (at + need <= s->size) {
-            *p = s->base + at;
-            return cudaSuccess;
+        size_t at = s->used.load();
+        while (at + need <= s->size) {
+            if (s->used.compare_exchange_weak(at, at + need)) {
+                *p = s->base + at;
+                return cudaSuccess;
+            }
         }
-        s->used.fetch_sub(need);  // exhausted (the estimate was short): an allocation of its own
+        // exhausted (the estimate was short): an allocation of its own
     }
     return cudaMalloc(p, bytes);
 }
