@@ -100,15 +100,19 @@ void sp_matrix_mg::sp_matrix_fill() {
 void sp_matrix_mg::sp_matrix_fill_diagonal() {
     delete[] diagonal;
     delete[] helper;
-    diagonal = new double[(size_t)nrow]();
-    helper = new double[(size_t)nrow]();
+    diagonal = new double[(size_t)std::max(nrow, 1)];  // zeroed by the threads below: they touch the pages first
+    helper = new double[(size_t)std::max(nrow, 1)];
 #pragma omp parallel for num_threads(options().threads) schedule(static)
-    for (int i = 0; i < nrow; i++)
+    for (int i = 0; i < nrow; i++) {
+        double d = 0.0;
         for (int j = rowptr[i]; j < rowptr[i + 1]; j++)
             if (colindex[j] == i) {
-                diagonal[i] = val[j];
+                d = val[j];
                 break;
             }
+        diagonal[i] = d;
+        helper[i] = 0.0;
+    }
 }
 
 sp_matrix_mg::~sp_matrix_mg() {
@@ -209,23 +213,35 @@ constexpr int PAT_SA_MAXROW = 512;  // distinct aggregates one fine row may touc
 // P is n x n_coarse with a single 1.0 per row.  The greedy sweep is inherently sequential, O(nnz).
 void HEM_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int l1) {
     const int n = A.nrow;
-    P = new sp_matrix_mg(n, 1, n);
+    P = new sp_matrix_mg();
+    P->nrow = n;
+    P->ncol = 1;
+    P->nnz = n;
+    P->rowptr = new int[(size_t)n + 1];
+    P->colindex = new int[(size_t)std::max(n, 1)];
+    P->val = new double[(size_t)std::max(n, 1)];
     int *agg = P->colindex;
-    std::fill(agg, agg + n, -1);
-    std::fill(P->val, P->val + n, 1.0);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+    for (int i = 0; i < n; i++) {  // the arrays are written here for the first time, by all threads
+        agg[i] = -1;
+        P->val[i] = 1.0;
+        P->rowptr[i] = i;
+    }
+    P->rowptr[n] = n;
     int next_id = 0;
     const int first = (l1 % 2 == 0) ? 0 : n - 1, step = (l1 % 2 == 0) ? 1 : -1;
+    const int *__restrict rp = A.rowptr, *__restrict ci = A.colindex;
+    const double *__restrict av = A.val;
     for (int t = 0, i = first; t < n; t++, i += step) {
         if (agg[i] != -1) continue;
         int mate = -1;
         double heaviest = 0.0;
-        for (int j = A.rowptr[i]; j < A.rowptr[i + 1]; j++) {
-            const int c = A.colindex[j];
-            const double w = std::fabs(A.val[j]);
-            if (agg[c] == -1 && w > heaviest && c != i) {
-                heaviest = w;
-                mate = c;
-            }
+        for (int j = rp[i]; j < rp[i + 1]; j++) {  // selects instead of branches: the outcome is data, not pattern
+            const int c = ci[j];
+            const double w = std::fabs(av[j]);
+            const bool take = (agg[c] == -1) & (w > heaviest) & (c != i);
+            heaviest = take ? w : heaviest;
+            mate = take ? c : mate;
         }
         if (mate != -1) {
             agg[i] = next_id;
@@ -235,7 +251,6 @@ void HEM_Prolongator(sp_matrix_mg &A, sp_matrix_mg *&P, int l1) {
     }
     for (int i = 0; i < n; i++)
         if (agg[i] == -1) agg[i] = next_id++;
-    for (int i = 0; i <= n; i++) P->rowptr[i] = i;
     P->ncol = next_id;
     P->nnz = n;
 }
@@ -439,6 +454,33 @@ struct Csr {
     }
 };
 
+// rp[0] = 0, rp[i + 1] holds a count on entry and the inclusive running sum on return (block sums, then offsets)
+void counts_to_offsets(std::vector<int> &rp) {
+    const long long n = (long long)rp.size() - 1;
+    const int nt = std::max(1, options().threads);
+    if (n < (1 << 16) || nt == 1) {
+        for (long long i = 0; i < n; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+        return;
+    }
+    std::vector<long long> block((size_t)nt + 1, 0);
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num(), n_t = omp_get_num_threads();
+        const long long lo = n * t / n_t, hi = n * (t + 1) / n_t;
+        long long sum = 0;
+        for (long long i = lo; i < hi; i++) sum += rp[(size_t)i + 1];
+        block[(size_t)t + 1] = sum;
+#pragma omp barrier
+#pragma omp single
+        for (int k = 0; k < n_t; k++) block[(size_t)k + 1] += block[k];
+        long long run = block[t];
+        for (long long i = lo; i < hi; i++) {
+            run += rp[(size_t)i + 1];
+            rp[(size_t)i + 1] = (int)run;
+        }
+    }
+}
+
 // row-wise (Gustavson) C = A * B.  The entries of a C row appear in first-touch order and each is accumulated in
 // traversal order, which fixes the rounding independently of the thread count.  Rows of the Galerkin products are
 // short (tens of entries), so the accumulator of a row is a small list searched linearly — it stays in L1, where a
@@ -489,7 +531,7 @@ void spgemm(int arow, const int *arp, const int *aci, const double *av, int bcol
             C.rp[i + 1] = cnt;
         }
     }
-    for (int i = 0; i < arow; i++) C.rp[i + 1] += C.rp[i];
+    counts_to_offsets(C.rp);
     C.alloc((size_t)C.rp[arow]);
 #pragma omp parallel num_threads(nt)
     {
@@ -568,6 +610,144 @@ void transpose(int nrow, int ncol, const int *rp, const int *ci, const double *v
     }
 }
 
+
+// C = P^T (A P) when P has exactly ONE entry per row (aggregation: HEM).  The two products collapse into one sweep over
+// the aggregates without A P or P^T ever being stored, yet every number is produced by the operations, in the order, of
+// the two general products above: per fine row i the sums s_i[col] = sum_j a_ij * p_j over the entries of the row that
+// fall into the same aggregate (first-touch order, accumulated in traversal order — row i of A P), then per aggregate c
+// its fine rows in ascending order (row c of the stable P^T) add p_i * s_i[col] into the coarse row, again first touch
+// first.  Same bits, half the memory traffic.  false: not applicable (P is not an aggregation, or a row outgrows the
+// small lists) — the caller runs the general products.
+bool aggregation_rap(int n, const int *arp, const int *aci, const double *av, int nc, const int *prp, const int *agg,
+                     const double *pv, Csr &C) {
+    constexpr int SMALL = 96, ROWMAX = 128;
+    const int nt = std::max(1, options().threads);
+    if (n == 0 || nc == 0 || prp[n] != n) return false;
+    int bad = 0;
+#pragma omp parallel for num_threads(nt) schedule(static) reduction(| : bad)
+    for (int i = 0; i < n; i++) bad |= (prp[i] != i) | (arp[i + 1] - arp[i] > ROWMAX) | (agg[i] < 0) | (agg[i] >= nc);
+    if (bad) return false;
+    // the fine rows of every aggregate, ascending
+    const double tt0 = omp_get_wtime();
+    std::vector<int> mrp((size_t)nc + 1, 0);
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int i = 0; i < n; i++) {
+#pragma omp atomic
+        mrp[(size_t)agg[i] + 1]++;
+    }
+    counts_to_offsets(mrp);
+    std::unique_ptr<int[]> mem(new int[(size_t)n]);
+    {
+        std::unique_ptr<int[]> cur(new int[(size_t)nc]);
+#pragma omp parallel num_threads(nt)
+        {
+#pragma omp for schedule(static)
+            for (int c = 0; c < nc; c++) cur[c] = mrp[c];
+#pragma omp for schedule(static)
+            for (int i = 0; i < n; i++) {
+                int d;
+#pragma omp atomic capture
+                d = cur[agg[i]]++;
+                mem[(size_t)d] = i;
+            }
+#pragma omp for schedule(static)
+            for (int c = 0; c < nc; c++)  // threads arrive in any order: ascending inside an aggregate (they are small)
+                for (int a = mrp[c] + 1; a < mrp[c + 1]; a++) {
+                    const int x = mem[a];
+                    int b = a - 1;
+                    while (b >= mrp[c] && mem[b] > x) {
+                        mem[b + 1] = mem[b];
+                        b--;
+                    }
+                    mem[b + 1] = x;
+                }
+        }
+    }
+    const double tt1 = omp_get_wtime();
+    C.nrow = nc;
+    C.ncol = nc;
+    C.rp.assign((size_t)nc + 1, 0);
+    int overflow = 0;
+#pragma omp parallel num_threads(nt) reduction(| : overflow)
+    {
+        int list[SMALL];
+#pragma omp for schedule(dynamic, 2048)
+        for (int c = 0; c < nc; c++) {
+            int cnt = 0;
+            for (int m = mrp[c]; m < mrp[c + 1] && cnt >= 0; m++) {
+                const int i = mem[m];
+                for (int j = arp[i]; j < arp[i + 1]; j++) {
+                    const int col = agg[aci[j]];
+                    int t = 0;
+                    while (t < cnt && list[t] != col) t++;
+                    if (t == cnt) {
+                        if (cnt == SMALL) {
+                            cnt = -1;
+                            break;
+                        }
+                        list[cnt++] = col;
+                    }
+                }
+            }
+            if (cnt < 0) {
+                overflow = 1;
+                cnt = 0;
+            }
+            C.rp[(size_t)c + 1] = cnt;
+        }
+    }
+    if (overflow) return false;
+    const double tt2 = omp_get_wtime();
+    counts_to_offsets(C.rp);
+    C.alloc((size_t)C.rp[nc]);
+    const double tt3 = omp_get_wtime();
+#pragma omp parallel num_threads(nt)
+    {
+        int col1[ROWMAX];
+        double s1[ROWMAX];
+#pragma omp for schedule(dynamic, 2048)
+        for (int c = 0; c < nc; c++) {
+            int *cc = C.ci.get() + C.rp[c];
+            double *cv = C.v.get() + C.rp[c];
+            int o = 0;
+            for (int m = mrp[c]; m < mrp[c + 1]; m++) {
+                const int i = mem[m];
+                int l1 = 0;  // row i of A P
+                for (int j = arp[i]; j < arp[i + 1]; j++) {
+                    const int k = aci[j], col = agg[k];
+                    const double prod = av[j] * pv[k];
+                    int t = 0;
+                    while (t < l1 && col1[t] != col) t++;
+                    if (t == l1) {
+                        col1[l1] = col;
+                        s1[l1] = prod;
+                        l1++;
+                    } else {
+                        s1[t] += prod;
+                    }
+                }
+                const double r = pv[i];  // the entry of P^T
+                for (int q = 0; q < l1; q++) {
+                    const int col = col1[q];
+                    const double x = r * s1[q];
+                    int t = 0;
+                    while (t < o && cc[t] != col) t++;
+                    if (t == o) {
+                        cc[o] = col;
+                        cv[o] = x;
+                        o++;
+                    } else {
+                        cv[t] += x;
+                    }
+                }
+            }
+        }
+    }
+    if (getenv("SPARSH_SETUP_TIMING"))
+        std::cout << "    fused: members " << tt1 - tt0 << " count " << tt2 - tt1 << " scan " << tt3 - tt2 << " fill " << omp_get_wtime() - tt3 << std::endl;
+    return true;
+}
+
 }  // namespace
 
 // Products that the device computed stay there until the next level has used them as its fine matrix (options().gpu_rap):
@@ -629,11 +809,19 @@ void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
             return;
         }  // else: a product row is too long for the device kernel — the host product below
     }
-    spgemm(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, AP);
-    double t1 = omp_get_wtime();
-    transpose(P1.nrow, P1.ncol, P1.rowptr, P1.colindex, P1.val, R);
-    double t2 = omp_get_wtime();
-    spgemm(R.nrow, R.rp.data(), R.ci.get(), R.v.get(), P1.ncol, AP.rp.data(), AP.ci.get(), AP.v.get(), C);
+    // aggregation prolongators (one entry per row: HEM) take the fused sweep, everything else the two general products;
+    // SPARSH_RAP_GENERAL=1 forces the latter (tests compare the two bit for bit)
+    const char *force_general = getenv("SPARSH_RAP_GENERAL");
+    const bool fused = !(force_general && atoi(force_general) != 0) &&
+                       aggregation_rap(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, C);
+    double t1 = omp_get_wtime(), t2 = t1;
+    if (!fused) {
+        spgemm(A.nrow, A.rowptr, A.colindex, A.val, P1.ncol, P1.rowptr, P1.colindex, P1.val, AP);
+        t1 = omp_get_wtime();
+        transpose(P1.nrow, P1.ncol, P1.rowptr, P1.colindex, P1.val, R);
+        t2 = omp_get_wtime();
+        spgemm(R.nrow, R.rp.data(), R.ci.get(), R.v.get(), P1.ncol, AP.rp.data(), AP.ci.get(), AP.v.get(), C);
+    }
     double t3 = omp_get_wtime();
     const int nc = P1.ncol, cnnz = C.rp[nc];
     Ac = new sp_matrix_mg();  // adopts the product's arrays (both sides use new[] / delete[])
@@ -649,7 +837,7 @@ void coarsen_matrix(sp_matrix_mg &A, sp_matrix_mg *&Ac, sp_matrix_mg &P1) {
     double t5 = omp_get_wtime();
     Ac->sp_matrix_fill_diagonal();
     if (tm)
-        std::cout << "  RAP: A*P " << t1 - t0 << " transpose " << t2 - t1 << " R*(AP) " << t3 - t2 << " alloc+copy " << t4 - t3
+        std::cout << (fused ? "  RAP (fused aggregation sweep " : "  RAP (general: A*P ") << t1 - t0 << " transpose " << t2 - t1 << " R*(AP) " << t3 - t2 << ") alloc+copy " << t4 - t3
                   << " sort " << t5 - t4 << " diag " << omp_get_wtime() - t5 << std::endl;
 }
 
@@ -698,6 +886,7 @@ void AMG_solver::reserve_levels(int nlevels) {
 static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
     const sparsh::Options &o = options();
     const double t0 = omp_get_wtime();
+    const bool timing = getenv("SPARSH_SETUP_TIMING") != nullptr;  // developer switch: where does the setup go?
     S.l = 0;
     S.reserve_levels(std::max(o.max_levels, 1));
     S.Av[0] = &A;  // borrowed, as in the reference (src/AMG_phases.cpp:40)
@@ -706,12 +895,14 @@ static void build_hierarchy(AMG_solver &S, sp_matrix_mg &A, bool colour) {
     int l = 0;
     while (S.Av[l]->nrow > o.coarse_upper && l < o.max_levels - 1 && l < S.capacity - 1) {
         if (o.print_setup) std::cout << "Level " << l << ":\t" << S.Av[l]->nrow << std::endl;
+        const double tp = omp_get_wtime();
         if (o.coarsening == sparsh::COARSEN_BECK)
             sequential::beck_prolongator(*S.Av[l], S.Pv[l]);
         else if (o.coarsening == sparsh::COARSEN_SA)
             sequential::SA_Prolongator(*S.Av[l], S.Pv[l], l);
         else
             sequential::HEM_Prolongator(*S.Av[l], S.Pv[l], l);
+        if (timing) std::cout << "  prolongator (" << S.Av[l]->nrow << " rows): " << omp_get_wtime() - tp << std::endl;
         parallel::coarsen_matrix(*S.Av[l], S.Av[l + 1], *S.Pv[l]);
         if (colour) {
             forget_device_product(S.Av[l + 1]);  // the reordering below makes the device copy stale

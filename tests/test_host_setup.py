@@ -508,6 +508,36 @@ def test_smoothed_aggregation_converges_faster(host, oracle):
     assert its["sa"][0] < its["hem"][0] and its["sa"][1] < its["hem"][1] and its["sa"][2] < its["hem"][2], its
 
 
+def test_fused_aggregation_product_equals_the_two_general_products(host, fixture_system, monkeypatch):
+    """parallel::coarsen_matrix (reference src/AMG_cycle_utilities.cpp:126-146): for a prolongator with one entry per row
+    (HEM) the host setup computes P^T (A P) in one sweep over the aggregates (setup.cpp: aggregation_rap).  It must give
+    the BITS of the two general row-wise products (SPARSH_RAP_GENERAL=1) on every level: same first-touch column order
+    before the sort, same accumulation order, same unfused arithmetic — on the bundled FE system, on a 3D grid (forward
+    and backward sweeps, singletons numbered last) and on a 2D grid."""
+    F, _ = fixture_system
+    mats = [host.HostMatrix.from_csr(F), host.HostMatrix.poisson3d(40, 36, 30), host.HostMatrix.poisson2d(150, 131)]
+    host.set_options(coarsening=0, coarse_upper=200, coarse_lower=50, max_levels=32, print_setup=0, threads=4)
+    try:
+        for M in mats:
+            monkeypatch.delenv("SPARSH_RAP_GENERAL", raising=False)
+            fused = host.HostAmg(M)
+            monkeypatch.setenv("SPARSH_RAP_GENERAL", "1")
+            general = host.HostAmg(M)
+            assert fused.nlevels == general.nlevels and fused.nlevels >= 4
+            for Lf, Lg in zip(fused.levels(), general.levels()):
+                for key in ("rowptr", "colindex", "val"):
+                    a, b = np.asarray(getattr(Lf["A"], key)), np.asarray(getattr(Lg["A"], key))
+                    assert a.shape == b.shape and a.tobytes() == b.tobytes(), key
+                assert np.asarray(Lf["diag"]).tobytes() == np.asarray(Lg["diag"]).tobytes()
+            fused.free()
+            general.free()
+    finally:
+        monkeypatch.delenv("SPARSH_RAP_GENERAL", raising=False)
+        host.set_options(coarsening=0, coarse_upper=4000, coarse_lower=2000, max_levels=6, print_setup=1)
+        for M in mats:
+            M.free()
+
+
 def _emulate_tma_tile_arithmetic(M, enc, row_begin=0, row_end=None):
     """Replays, in numpy, the index arithmetic of csr_pattern_tma_kernel (spmv.cu) for every tile: which x ranges the
     bulk copies fetch, where they land in shared memory, and which shared-memory slot each (row, entry) reads.
