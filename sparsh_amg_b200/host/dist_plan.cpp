@@ -14,6 +14,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -30,10 +31,29 @@ using sparsh::options;
 
 namespace {
 
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big arrays below are written in
+// full by the threads right after (a value-initialising resize clears hundreds of MB on one thread first)
+template <class T>
+struct DefaultInit : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = DefaultInit<U>;
+    };
+    template <class U>
+    void construct(U *p) noexcept {
+        ::new (static_cast<void *>(p)) U;
+    }
+    template <class U, class... Args>
+    void construct(U *p, Args &&...a) {
+        ::new (static_cast<void *>(p)) U(std::forward<Args>(a)...);
+    }
+};
+
 struct OpLocal {
     int nrow = 0, ncol_local = 0, nhalo = 0;
-    std::vector<int> rp, ci;
-    std::vector<double> v, diag;
+    std::vector<int> rp;
+    std::vector<int, DefaultInit<int>> ci;
+    std::vector<double, DefaultInit<double>> v, diag;
     std::vector<int> send_rank, send_ptr, send_idx, recv_rank, recv_ptr;
     std::vector<int> halo_global;  // global ids of the halo entries, in halo order (tests)
     int ib = 0, ie = 0;
@@ -84,7 +104,25 @@ void finish_space(Space &s, int nranks) {
     const int n = (int)s.owner.size();
     s.loc.resize(n);
     s.count.assign(nranks, 0);
-    for (int g = 0; g < n; g++) s.loc[g] = s.count[s.owner[g]]++;
+    // loc[g] = number of ids below g with the same owner: per-chunk counts, offsets over the chunks, then the ids
+    const int nt = std::max(1, options().threads);
+    std::vector<int> chunk_count((size_t)(nt + 1) * nranks, 0);
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num(), n_t = omp_get_num_threads();
+        const int g0 = (int)((long long)n * t / n_t), g1 = (int)((long long)n * (t + 1) / n_t);
+        int *mine = chunk_count.data() + (size_t)(t + 1) * nranks;
+        for (int g = g0; g < g1; g++) mine[s.owner[g]]++;
+#pragma omp barrier
+#pragma omp single
+        for (int k = 0; k < n_t; k++)
+            for (int r = 0; r < nranks; r++) chunk_count[(size_t)(k + 1) * nranks + r] += chunk_count[(size_t)k * nranks + r];
+        std::vector<int> run(chunk_count.begin() + (size_t)t * nranks, chunk_count.begin() + (size_t)(t + 1) * nranks);
+        for (int g = g0; g < g1; g++) s.loc[g] = run[s.owner[g]]++;
+#pragma omp barrier
+#pragma omp single
+        for (int r = 0; r < nranks; r++) s.count[r] = chunk_count[(size_t)n_t * nranks + r];
+    }
 }
 
 // rows owned by `rank` of the global CSR (row space rs, column space cs) -> local operator + exchange plan
@@ -99,12 +137,22 @@ void build_op(int nrow_g, const int *rp, const int *ci, const double *v, const d
     // halo = referenced columns owned elsewhere, ordered by (owner, global id)
     std::vector<std::pair<int, int>> halo;
     op.rp.assign((size_t)op.nrow + 1, 0);
-    for (int k = 0; k < op.nrow; k++) {
-        const int g = rows[k];
-        op.rp[k + 1] = op.rp[k] + (rp[g + 1] - rp[g]);
-        for (int j = rp[g]; j < rp[g + 1]; j++)
-            if (cs.owner[ci[j]] != rank) halo.emplace_back(cs.owner[ci[j]], ci[j]);
+#pragma omp parallel num_threads(options().threads)
+    {
+        std::vector<std::pair<int, int>> mine;
+#pragma omp for schedule(static) nowait
+        for (int k = 0; k < op.nrow; k++) {
+            const int g = rows[k];
+            op.rp[k + 1] = rp[g + 1] - rp[g];
+            for (int j = rp[g]; j < rp[g + 1]; j++)
+                if (cs.owner[ci[j]] != rank) mine.emplace_back(cs.owner[ci[j]], ci[j]);
+        }
+        std::sort(mine.begin(), mine.end());
+        mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+#pragma omp critical
+        halo.insert(halo.end(), mine.begin(), mine.end());
     }
+    for (int k = 0; k < op.nrow; k++) op.rp[k + 1] += op.rp[k];
     std::sort(halo.begin(), halo.end());
     halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
     op.nhalo = (int)halo.size();
@@ -251,12 +299,20 @@ void *sparsh_host_dist_plan(void *Sv, int nranks, int rank, int tail_threshold) 
     for (int l = 0; l < nd; l++) {
         const sp_matrix_mg *P = S->Pv[l];
         std::vector<int> &own = sp[l + 1].owner;
-        own.assign((size_t)P->ncol, -1);
-        for (int i = 0; i < P->nrow; i++)  // ascending i: the first fine row of every coarse row decides
-            for (int j = P->rowptr[i]; j < P->rowptr[i + 1]; j++)
-                if (own[P->colindex[j]] < 0) own[P->colindex[j]] = sp[l].owner[i];
-        for (int &o : own)
-            if (o < 0) o = 0;  // a coarse row nobody interpolates from (cannot happen with HEM/Beck)
+        // the first (lowest) fine row of every coarse row decides: a minimum, so the threads may arrive in any order
+        std::vector<int> first((size_t)P->ncol, INT_MAX);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+        for (int i = 0; i < P->nrow; i++)
+            for (int j = P->rowptr[i]; j < P->rowptr[i + 1]; j++) {
+                int *slot = &first[P->colindex[j]];
+                int seen = __atomic_load_n(slot, __ATOMIC_RELAXED);
+                while (i < seen && !__atomic_compare_exchange_n(slot, &seen, i, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                }
+            }
+        own.resize((size_t)P->ncol);
+#pragma omp parallel for num_threads(options().threads) schedule(static)
+        for (int c = 0; c < P->ncol; c++)  // (a coarse row nobody interpolates from cannot happen with HEM/Beck: rank 0)
+            own[c] = first[c] == INT_MAX ? 0 : sp[l].owner[first[c]];
         finish_space(sp[l + 1], nranks);
     }
     const bool tm = getenv("SPARSH_SETUP_TIMING") != nullptr;
